@@ -1,0 +1,51 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference module (run in the build container).
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+For each preset and input distribution: weights = oracle/weights.make_state_dict(preset, seed=5)
+loaded (strict) into the reference's EgoTAPAutoEncoder, inputs =
+egotap_b200.synthetic.synthetic_heatmaps(preset, 2, seed=1234, kind).  Stored: the reference's
+pose output and the propagation-network taps the reference itself exposes as attributes
+(``skel_inputs``, ``skel_embed``; reference model/net_architecture.py:725,727).
+Weights and inputs are regenerated from their seeds at test time (388 MB would not fit in git).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+import ref_shim  # noqa: E402
+import weights  # noqa: E402
+from egotap_b200.synthetic import synthetic_heatmaps  # noqa: E402
+
+WEIGHT_SEED, INPUT_SEED, BATCH = 5, 1234, 2
+
+
+def main():
+    for preset in ("UnrealEgo", "EgoCap"):
+        net = ref_shim.build_reference_net(preset)
+        net.load_state_dict(weights.make_state_dict(preset, seed=WEIGHT_SEED), strict=True)
+        for kind in ("gauss", "uniform"):
+            x = synthetic_heatmaps(preset, BATCH, seed=INPUT_SEED, kind=kind)
+            with torch.no_grad():
+                pose, rot, indep, hm = net(x)
+            out = dict(pose=pose.detach().numpy(),
+                       skel_inputs=net.skel_inputs.detach().numpy(),      # (J, B, 512) = [pos|limb] embeds
+                       skel_embed=net.skel_embed.detach().numpy(),        # (J, B, 512)
+                       aux_shapes=np.array([rot.shape[1], indep.shape[1], hm.shape[1]]),
+                       aux_absmax=np.array([rot.abs().max().item(), indep.abs().max().item(), hm.abs().max().item()]),
+                       input_checksum=np.array([x.double().sum().item(), x.double().pow(2).sum().item()]),
+                       meta=np.array([WEIGHT_SEED, INPUT_SEED, BATCH]))
+            path = os.path.join(HERE, "ref_%s_%s.npz" % (preset, kind))
+            np.savez_compressed(path, **out)
+            print("wrote", path, pose.shape)
+
+
+if __name__ == "__main__":
+    main()

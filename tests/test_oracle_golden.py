@@ -1,0 +1,67 @@
+"""Oracle (oracle/egotap_oracle.py) vs the committed outputs of the unmodified reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import egotap_oracle as orc
+from egotap_b200.synthetic import synthetic_heatmaps
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = [(p, k) for p in ("UnrealEgo", "EgoCap") for k in ("gauss", "uniform")]
+
+
+@pytest.mark.parametrize("preset,kind", CASES)
+def test_oracle_matches_reference_golden(preset, kind, state_dicts):
+    gold = np.load(os.path.join(GOLD, "ref_%s_%s.npz" % (preset, kind)))
+    wseed, iseed, batch = (int(v) for v in gold["meta"])
+    assert wseed == 5
+    x = synthetic_heatmaps(preset, batch, seed=iseed, kind=kind)
+    # the regenerated input is the one the golden was made from
+    np.testing.assert_allclose([x.double().sum().item(), x.double().pow(2).sum().item()],
+                               gold["input_checksum"], rtol=1e-12)
+    taps = {}
+    with torch.no_grad():
+        pose = orc.forward(state_dicts(preset), x, preset, taps=taps)
+    ref = torch.from_numpy(gold["pose"])
+    rep = orc.parity_report(pose, ref)
+    # fp32 summation-order noise only (bound: 20x what was observed when the golden was made)
+    assert rep["rel"] < 2e-5 and rep["mpjpe_delta_mm"] < 1e-4, rep
+    skel_in = torch.cat([taps["pos_embed"], taps["rot_embed"]], -1).transpose(0, 1)
+    np.testing.assert_allclose(skel_in.numpy(), gold["skel_inputs"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(taps["skel"].transpose(0, 1).numpy(), gold["skel_embed"], atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("preset", ["UnrealEgo", "EgoCap"])
+def test_aux_outputs_are_zeros_with_reference_shapes(preset, state_dicts):
+    gold = np.load(os.path.join(GOLD, "ref_%s_gauss.npz" % preset))
+    x = synthetic_heatmaps(preset, 1, seed=1, kind="uniform")
+    with torch.no_grad():
+        pose, rot, indep, hm = orc.forward_full(state_dicts(preset), x, preset)
+    assert [rot.shape[1], indep.shape[1], hm.shape[1]] == list(gold["aux_shapes"])
+    assert float(np.abs(gold["aux_absmax"]).max()) == 0.0
+    assert rot.abs().max() == 0 and indep.abs().max() == 0 and hm.abs().max() == 0
+    assert hm.shape == x.shape
+
+
+def test_chain_not_tree(state_dicts):
+    """The reference's 'kinematic tree' walk is behaviourally a chain: a true tree
+    walk must NOT reproduce the golden."""
+    preset = "UnrealEgo"
+    gold = np.load(os.path.join(GOLD, "ref_UnrealEgo_gauss.npz"))
+    x = synthetic_heatmaps(preset, 2, seed=1234, kind="gauss")
+    parents = [0, 0, 1, 1, 2, 3, 4, 5, 2, 3, 8, 9, 10, 11, 12, 13]
+    with torch.no_grad():
+        tree = orc.forward(state_dicts(preset), x, preset, tree_parents=parents)
+    assert orc.parity_report(tree, torch.from_numpy(gold["pose"]))["rel"] > 1e-2
+
+
+def test_batch_rows_are_independent(state_dicts):
+    preset = "EgoCap"
+    x = synthetic_heatmaps(preset, 3, seed=7, kind="gauss")
+    with torch.no_grad():
+        full = orc.forward(state_dicts(preset), x, preset)
+        one = orc.forward(state_dicts(preset), x[1:2], preset)
+    assert (full[1:2] - one).abs().max() < 1e-5
