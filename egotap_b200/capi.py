@@ -1,0 +1,118 @@
+"""ctypes binding of ``libegotap_b200.so`` (C ABI declared in ``include/egotap_b200.h``).
+
+This is the only place Python touches the native library.  There is no fallback: if the shared
+library is missing the import raises, and every compute entry needs a CUDA device.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libegotap_b200.so")
+
+PREC_BF16X3, PREC_BF16 = 0, 1
+PRESET_ID = {"UnrealEgo": 0, "EgoCap": 1}
+ACT_NONE, ACT_GELU, ACT_LRELU = 0, 1, 2
+STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP = 0, 1, 2
+
+# every symbol include/egotap_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
+    "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
+    "egotap_b200_split_bf16",
+]
+
+
+class Operand(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_longlong), ("rows", C.c_longlong),
+                ("g0_count", C.c_longlong), ("g0_stride", C.c_longlong),
+                ("g1_count", C.c_longlong), ("g1_stride", C.c_longlong)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("scale", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int),
+                ("resid", C.c_void_p), ("resid_ld", C.c_longlong), ("resid_mod", C.c_int),
+                ("rows_in", C.c_int), ("rows_out", C.c_int), ("group_rows", C.c_longlong),
+                ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+                ("ldo", C.c_longlong), ("col_off", C.c_int), ("store", C.c_int),
+                ("qk_cols", C.c_int), ("tokens", C.c_int), ("vt_hi", C.c_void_p), ("vt_lo", C.c_void_p),
+                ("J", C.c_int)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [("a", Operand), ("b", Operand), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("groups", C.c_int), ("precision", C.c_int), ("variant", C.c_int), ("epi", Epilogue)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the native library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("egotap_b200: native library %s is missing -- run "
+                               "`python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.egotap_b200_last_error.restype = C.c_char_p
+        L.egotap_b200_launch_count.restype = C.c_longlong
+        L.egotap_b200_gemm_variant_name.restype = C.c_char_p
+        L.egotap_b200_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
+        L.egotap_b200_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("egotap_b200: %s failed (%d): %s" % (what, rc, lib().egotap_b200_last_error().decode()))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("egotap_b200 has no CPU path: got a %s tensor" % t.device)
+
+
+def split_bf16(x, want_lo=True):
+    """fp32 CUDA tensor -> (hi, lo) bf16 tensors with x ~= hi + lo."""
+    import torch
+    require_cuda(x)
+    x = x.contiguous()
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo = torch.empty_like(x, dtype=torch.bfloat16) if want_lo else None
+    check(lib().egotap_b200_split_bf16(x.data_ptr(), hi.data_ptr(), _ptr(lo), x.numel(), current_stream()), "split_bf16")
+    return hi, lo
+
+
+def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0), a_rows=None,
+         b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
+    """Op-level entry used by the tests: D = epi(A @ B^T).  ``epi`` keys mirror ``egotap_epilogue``;
+    tensor-valued keys take CUDA tensors."""
+    d = Gemm()
+    d.a = Operand(_ptr(a_hi), _ptr(a_lo), lda or K, a_rows or M, *a_group)
+    d.b = Operand(_ptr(b_hi), _ptr(b_lo), ldb or K, b_rows or N, *b_group)
+    d.M, d.N, d.K, d.groups, d.precision, d.variant = M, N, K, groups, precision, variant
+    e = d.epi
+    e.alpha = float(epi.pop("alpha", 1.0))
+    for name in ("scale", "bias", "resid", "out_f32", "out_hi", "out_lo", "vt_hi", "vt_lo"):
+        t = epi.pop(name, None)
+        require_cuda(t)
+        setattr(e, name, _ptr(t))
+    for name in ("act", "resid_ld", "resid_mod", "rows_in", "rows_out", "group_rows", "ldo", "col_off", "store",
+                 "qk_cols", "tokens", "J"):
+        setattr(e, name, int(epi.pop(name, 0)))
+    if epi:
+        raise TypeError("unknown epilogue fields: %s" % sorted(epi))
+    if e.ldo == 0:
+        e.ldo = N
+    check(lib().egotap_b200_gemm(C.byref(d), current_stream()), "gemm")

@@ -1,0 +1,307 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[g][m][n] = epilogue( sum_k A[g][m][k] * B[g][n][k] )        A, B: bf16, K-major; accumulate fp32 in TMEM
+//
+// * operands arrive by TMA (4-D tiled maps, 128-byte swizzle) into a multi-stage shared-memory ring
+// * one elected thread issues tcgen05.mma; CG = 2 pairs two SMs on one 256 x BN tile (cta_group::2)
+// * NSPLIT = 3 is the error-compensated mode: A = Ah + Al, B = Bh + Bl (bf16 hi/lo splits) and
+//   D = Ah*Bh + Ah*Bl + Al*Bh, which restores ~16 mantissa bits per operand (fp32-parity mode);
+//   NSPLIT = 1 is the plain bf16-operand mode
+// * accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
+// * the epilogue (bias / scale-shift / GELU / LeakyReLU / residual / re-layout / hi-lo split) is fused
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// (warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32), so 4 consecutive warps cover all 128 lanes).
+#pragma once
+#include "ptx.cuh"
+
+namespace eb {
+
+enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
+enum : int { STORE_ROWMAJOR = 0, STORE_QKV = 1, STORE_JOINT_REGROUP = 2 };
+
+struct EpiParams {
+  float alpha;              // v = acc * alpha
+  const float* scale;       // v *= scale[n]            (nullable)
+  const float* bias;        // v += bias[n]             (nullable)
+  int act;                  // ACT_*
+  const float* resid;       // v += resid[rrow][n]      (nullable); rrow = resid_mod ? m % resid_mod : out row
+  long long resid_ld;
+  int resid_mod;
+  int rows_in, rows_out;    // out row = g*group_rows + (m / rows_in) * rows_out + m % rows_in  (rows_in == 0: m)
+  long long group_rows;
+  float* out_f32;           // any subset of the three outputs may be set
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ldo;
+  int col_off;
+  int store;                // STORE_*
+  // STORE_QKV: columns [0, qk_cols) row-major as above; columns [qk_cols, N) are V and are written transposed
+  // per (frame, head): vt[((frame*heads + h)*128 + d) * tokens + tok]
+  int qk_cols, tokens;
+  __nv_bfloat16* vt_hi;
+  __nv_bfloat16* vt_lo;
+  // STORE_JOINT_REGROUP: m = frame*2J + view*J + j  ->  out row = frame*J + j, column += view*N
+  int J;
+};
+
+struct GemmShape {
+  int M, N, K;      // per group
+  int groups;       // tiles enumerate (g, m_blk, n_blk), n fastest
+  int gdiv;         // TMA coords: c2 = g % gdiv, c3 = g / gdiv
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void epi_apply(const EpiParams& p, int g, int m, int n0, int N, uint32_t (&r)[32]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (p.scale) {
+    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 s = __ldg(s4 + j);
+      v[4 * j] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
+    }
+  }
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  }
+  long long orow;
+  int col = n0 + p.col_off;
+  if (p.store == STORE_JOINT_REGROUP) {
+    int frame = m / (2 * p.J), rem = m % (2 * p.J);
+    int view = rem / p.J, j = rem % p.J;
+    orow = (long long)frame * p.J + j;
+    col += view * N;
+  } else {
+    orow = (p.rows_in > 0) ? (long long)(m / p.rows_in) * p.rows_out + (m % p.rows_in) : (long long)m;
+    orow += (long long)g * p.group_rows;
+  }
+  if (p.resid) {
+    long long rrow = p.resid_mod > 0 ? (long long)(m % p.resid_mod) : orow;
+    const float4* r4 = reinterpret_cast<const float4*>(p.resid + rrow * p.resid_ld + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t = r4[j];
+      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+    }
+  }
+  if (p.store == STORE_QKV && n0 >= p.qk_cols) {
+    // V, transposed store: for a fixed column the 32 lanes of the warp hold 32 consecutive tokens
+    int frame = m / p.tokens, tok = m % p.tokens;
+    int hd = n0 - p.qk_cols;  // h*128 + d0
+    long long base = ((long long)frame * (N - p.qk_cols) + hd) * p.tokens + tok;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v[j], hi, lo);
+      p.vt_hi[base + (long long)j * p.tokens] = hi;
+      if (p.vt_lo) p.vt_lo[base + (long long)j * p.tokens] = lo;
+    }
+    return;
+  }
+  if (p.out_f32) {
+    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (p.out_hi) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * j], h0, l0);
+      split_bf16(v[2 * j + 1], h1, l1);
+      h[j] = pack_bf16x2(h0, h1);
+      l[j] = pack_bf16x2(l0, l1);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow * p.ldo + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    if (p.out_lo) {
+      uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow * p.ldo + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ol[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    }
+  }
+}
+
+template <int CG, int BN, int NSPLIT, int STAGES>
+struct GemmCfg {
+  static constexpr int BM = 128;                     // rows per CTA (tile rows = BM * CG)
+  static constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
+  static constexpr int BNL = BN / CG;                // B rows loaded by each CTA
+  static constexpr int NOPS = (NSPLIT == 1) ? 1 : 2; // hi (+ lo) copies of each operand
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BNL * BK * 2;
+  static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
+  static constexpr int THREADS = 192;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int CG, int BN, int NSPLIT, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+               const GemmShape s, const EpiParams ep) {
+  using C = GemmCfg<CG, BN, NSPLIT, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = (CG == 2) ? int(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  const int nM = (s.M + C::BM * CG - 1) / (C::BM * CG);
+  const int nN = (s.N + BN - 1) / BN;
+  const int nK = s.K / C::BK;
+  const int num_tiles = s.groups * nM * nN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmBh);
+    if (NSPLIT > 1) { tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int n_blk = tile % nN; const int t2 = tile / nN;
+        const int m_blk = t2 % nM;   const int g = t2 / nM;
+        const int g0 = g % s.gdiv, g1 = g / s.gdiv;
+        const int row_a = m_blk * C::BM * CG + cta_rank * C::BM;
+        const int row_b = n_blk * BN + cta_rank * C::BNL;
+        for (int kb = 0; kb < nK; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::NOPS * C::A_BYTES;
+          if (CG == 1) {
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            tma_load_4d(sa, &tmAh, &full[stage], kb * C::BK, row_a, g0, g1);
+            tma_load_4d(sb, &tmBh, &full[stage], kb * C::BK, row_b, g0, g1);
+            if (NSPLIT > 1) {
+              tma_load_4d(sa + C::A_BYTES, &tmAl, &full[stage], kb * C::BK, row_a, g0, g1);
+              tma_load_4d(sb + C::B_BYTES, &tmBl, &full[stage], kb * C::BK, row_b, g0, g1);
+            }
+          } else {
+            // both CTAs load their halves; all bytes are accounted on the leader's barrier
+            if (cta_rank == 0) mbar_expect_tx(&full[stage], C::STAGE_BYTES * 2);
+            tma_load_4d_2sm(sa, &tmAh, &full[stage], kb * C::BK, row_a, g0, g1);
+            tma_load_4d_2sm(sb, &tmBh, &full[stage], kb * C::BK, row_b, g0, g1);
+            if (NSPLIT > 1) {
+              tma_load_4d_2sm(sa + C::A_BYTES, &tmAl, &full[stage], kb * C::BK, row_a, g0, g1);
+              tma_load_4d_2sm(sb + C::B_BYTES, &tmBl, &full[stage], kb * C::BK, row_b, g0, g1);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(C::BM * CG, BN);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < nK; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint32_t b_hi = a_hi + C::NOPS * C::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < C::BK / 16; ++k) {
+              const uint64_t dah = make_sdesc_sw128(a_hi + k * 32, 16, 1024);
+              const uint64_t dbh = make_sdesc_sw128(b_hi + k * 32, 16, 1024);
+              umma_bf16<CG>(d_tmem, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (NSPLIT > 1) {
+                const uint64_t dal = make_sdesc_sw128(a_hi + C::A_BYTES + k * 32, 16, 1024);
+                const uint64_t dbl = make_sdesc_sw128(b_hi + C::B_BYTES + k * 32, 16, 1024);
+                umma_bf16<CG>(d_tmem, dah, dbl, idesc, 1u);
+                umma_bf16<CG>(d_tmem, dal, dbh, idesc, 1u);
+              }
+            }
+            umma_commit<CG>(&empty[stage]);
+            if (kb == nK - 1) umma_commit<CG>(&tfull[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int n_blk = tile % nN; const int t2 = tile / nN;
+      const int m_blk = t2 % nM;   const int g = t2 / nM;
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const int m = m_blk * C::BM * CG + cta_rank * C::BM + q * 32 + lane;
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= s.N) break;
+        uint32_t r[32];
+        tmem_ld32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        if (m < s.M) epi_apply(ep, g, m, n0, s.N, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace eb

@@ -1,0 +1,137 @@
+// Host launcher + C-ABI entry for the tcgen05 GEMM (gemm.cuh).
+#include "gemm.cuh"
+#include "host_util.cuh"
+#include "internal.h"
+
+namespace eb {
+
+template <int CG, int BN, int NS, int ST>
+static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
+  using C = GemmCfg<CG, BN, NS, ST>;
+  auto kern = gemm_tc_kernel<CG, BN, NS, ST>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int nM = (s.M + C::BM * CG - 1) / (C::BM * CG);
+  const int nN = (s.N + BN - 1) / BN;
+  const long long tiles = (long long)s.groups * nM * nN;
+  long long nclusters = num_sms() / CG;
+  if (tiles < nclusters) nclusters = tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(nclusters * CG));
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], s, ep));
+  EB_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+struct Variant {
+  const char* name;
+  int cg, bn, nsplit;
+  int (*launch)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);
+};
+
+static const Variant kVariants[] = {
+    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>},
+    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>},
+    {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>},
+    {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>},
+    {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>},
+    {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>},
+};
+static const int kNumVariants = int(sizeof(kVariants) / sizeof(kVariants[0]));
+
+static int g_prefer_cg = -1;
+static int prefer_cg() {
+  if (g_prefer_cg < 0) {
+    const char* e = getenv("EGOTAP_GEMM_CG");
+    g_prefer_cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_prefer_cg;
+}
+
+int pick_variant(int M, int N, int groups, int nsplit) {
+  const bool wide = (N % 256 == 0) || N > 256;
+  if (!wide) return nsplit == 3 ? 1 : 0;
+  // the paired-SM tile wants enough 256-row tiles to fill 74 clusters reasonably
+  const long long tiles2 = (long long)groups * ((M + 255) / 256) * ((N + 255) / 256);
+  if (prefer_cg() == 2 && M >= 256 && tiles2 >= 16) return nsplit == 3 ? 5 : 4;
+  return nsplit == 3 ? 3 : 2;
+}
+
+int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, const EpiParams& ep, int nsplit,
+             int variant, cudaStream_t stream) {
+  EB_REQUIRE(s.M > 0 && s.N > 0 && s.K > 0 && s.groups > 0, "gemm: bad shape M %d N %d K %d groups %d", s.M, s.N, s.K,
+             s.groups);
+  EB_REQUIRE(s.K % 64 == 0, "gemm: K (%d) must be a multiple of 64", s.K);
+  EB_REQUIRE(s.N % 32 == 0, "gemm: N (%d) must be a multiple of 32", s.N);
+  EB_REQUIRE(nsplit == 1 || nsplit == 3, "gemm: nsplit must be 1 or 3");
+  EB_REQUIRE(a.hi && b.hi, "gemm: null operand");
+  EB_REQUIRE(nsplit == 1 || (a.lo && b.lo), "gemm: bf16x3 mode needs lo parts of both operands");
+  if (variant < 0) variant = pick_variant(s.M, s.N, s.groups, nsplit);
+  EB_REQUIRE(variant < kNumVariants, "gemm: variant %d out of range", variant);
+  const Variant& v = kVariants[variant];
+  EB_REQUIRE(v.nsplit == nsplit, "gemm: variant %s does not match nsplit %d", v.name, nsplit);
+  CUtensorMap tm[4];
+  int rc;
+  const int box_b = v.bn / v.cg;
+  if ((rc = make_operand_tmap(&tm[0], a.hi, s.K, a.rows, a.ld, a.g0_count, a.g0_stride, a.g1_count, a.g1_stride, 128)))
+    return rc;
+  if ((rc = make_operand_tmap(&tm[2], b.hi, s.K, b.rows, b.ld, b.g0_count, b.g0_stride, b.g1_count, b.g1_stride, box_b)))
+    return rc;
+  if (nsplit == 3) {
+    if ((rc = make_operand_tmap(&tm[1], a.lo, s.K, a.rows, a.ld, a.g0_count, a.g0_stride, a.g1_count, a.g1_stride, 128)))
+      return rc;
+    if ((rc = make_operand_tmap(&tm[3], b.lo, s.K, b.rows, b.ld, b.g0_count, b.g0_stride, b.g1_count, b.g1_stride, box_b)))
+      return rc;
+  } else {
+    tm[1] = tm[0];
+    tm[3] = tm[2];
+  }
+  GemmShape sh = s;
+  if (sh.gdiv <= 0) sh.gdiv = int(a.g0_count > 0 ? a.g0_count : 1);
+  return v.launch(tm, sh, ep, stream);
+}
+
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" int egotap_b200_gemm_num_variants(void) { return kNumVariants; }
+extern "C" const char* egotap_b200_gemm_variant_name(int v) {
+  return (v >= 0 && v < kNumVariants) ? kVariants[v].name : "";
+}
+
+extern "C" int egotap_b200_gemm(const egotap_gemm* d, void* stream) {
+  if (!d) return fail(EGOTAP_E_ARG, "gemm: null descriptor");
+  GemmOperand a{(const __nv_bfloat16*)d->a.hi, (const __nv_bfloat16*)d->a.lo, d->a.ld, d->a.rows,
+                d->a.g0_count, d->a.g0_stride, d->a.g1_count, d->a.g1_stride};
+  GemmOperand b{(const __nv_bfloat16*)d->b.hi, (const __nv_bfloat16*)d->b.lo, d->b.ld, d->b.rows,
+                d->b.g0_count, d->b.g0_stride, d->b.g1_count, d->b.g1_stride};
+  GemmShape s{d->M, d->N, d->K, d->groups, 0};
+  const egotap_epilogue& e = d->epi;
+  EpiParams ep;
+  ep.alpha = e.alpha; ep.scale = e.scale; ep.bias = e.bias; ep.act = e.act;
+  ep.resid = e.resid; ep.resid_ld = e.resid_ld; ep.resid_mod = e.resid_mod;
+  ep.rows_in = e.rows_in; ep.rows_out = e.rows_out; ep.group_rows = e.group_rows;
+  ep.out_f32 = e.out_f32; ep.out_hi = (__nv_bfloat16*)e.out_hi; ep.out_lo = (__nv_bfloat16*)e.out_lo;
+  ep.ldo = e.ldo; ep.col_off = e.col_off; ep.store = e.store;
+  ep.qk_cols = e.qk_cols; ep.tokens = e.tokens;
+  ep.vt_hi = (__nv_bfloat16*)e.vt_hi; ep.vt_lo = (__nv_bfloat16*)e.vt_lo; ep.J = e.J;
+  EB_REQUIRE(ep.out_f32 || ep.out_hi || (ep.store == STORE_QKV && ep.vt_hi), "gemm: no output pointer");
+  EB_REQUIRE(ep.ldo % 8 == 0 && ep.col_off % 32 == 0, "gemm: ldo %% 8 and col_off %% 32 must be 0");
+  const int nsplit = d->precision == EGOTAP_PREC_BF16 ? 1 : 3;
+  return gemm_run(a, b, s, ep, nsplit, d->variant, (cudaStream_t)stream);
+}

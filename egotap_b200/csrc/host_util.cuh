@@ -1,0 +1,101 @@
+// Host-side helpers: error plumbing, TMA descriptor creation, launch accounting.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/egotap_b200.h"
+
+namespace eb {
+
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> c{0};
+  return c;
+}
+
+#define EB_CUDA(expr)                                                                           \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return eb::fail(int(_e), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define EB_CHECK_LAUNCH(name)                                                                   \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return eb::fail(int(_e), "launch of %s failed: %s", name, cudaGetErrorString(_e));        \
+    eb::launch_counter().fetch_add(1, std::memory_order_relaxed);                               \
+  } while (0)
+
+#define EB_REQUIRE(cond, ...)                                   \
+  do {                                                          \
+    if (!(cond)) return eb::fail(EGOTAP_E_ARG, __VA_ARGS__);    \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map [g1][g0][rows][K] (K contiguous), box = 64 x box_rows x 1 x 1, 128-byte swizzle.
+inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, long long rows, long long ld,
+                             long long g0_count, long long g0_stride, long long g1_count, long long g1_stride,
+                             int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(EGOTAP_E_DRIVER, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if (g0_count < 1) g0_count = 1;
+  if (g1_count < 1) g1_count = 1;
+  if (g0_stride <= 0) g0_stride = rows * ld;
+  if (g1_stride <= 0) g1_stride = g0_stride * g0_count;
+  cuuint64_t dims[4] = {cuuint64_t(K), cuuint64_t(rows), cuuint64_t(g0_count), cuuint64_t(g1_count)};
+  cuuint64_t strides[3] = {cuuint64_t(ld) * 2, cuuint64_t(g0_stride) * 2, cuuint64_t(g1_stride) * 2};
+  cuuint32_t box[4] = {64, cuuint32_t(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return fail(EGOTAP_E_ARG, "TMA operand must be 16-byte aligned (base %p ld %lld)", base, ld);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(EGOTAP_E_DRIVER, "cuTensorMapEncodeTiled failed (%d): K %lld rows %lld ld %lld box %d", int(r), K,
+                rows, ld, box_rows);
+  return 0;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace eb

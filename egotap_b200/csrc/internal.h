@@ -1,0 +1,26 @@
+// Internal (non-ABI) interfaces shared by the translation units of libegotap_b200.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace eb {
+
+struct EpiParams;
+struct GemmShape;
+
+struct GemmOperand {
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  long long ld;
+  long long rows;
+  long long g0_count, g0_stride, g1_count, g1_stride;
+};
+
+int pick_variant(int M, int N, int groups, int nsplit);
+int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, const EpiParams& ep, int nsplit,
+             int variant, cudaStream_t stream);
+
+// kernels.cu
+int split_bf16_run(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t stream);
+
+}  // namespace eb

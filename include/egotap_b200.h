@@ -1,0 +1,100 @@
+/* egotap_b200 -- C ABI of the B200-native EgoTAP heatmap->3D lifting path.
+ *
+ * The reference (tho-kn/EgoTAP) is pure Python/PyTorch and has no FFI of its own: the seam a
+ * replacement plugs into is the factory `define_AutoEncoder(opt, model)`
+ * (reference model/network.py:24-33) plus the nn.Module protocol of `EgoTAPAutoEncoder`
+ * (reference model/net_architecture.py:579-758).  The Python module in egotap_b200/ mirrors that
+ * surface and forwards every piece of arithmetic to the entry points below through ctypes
+ * (INTEGRATION.md shows the binding).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name says `host`; `stream` is a cudaStream_t
+ *   - every function returns 0 on success, a negative EGOTAP_E_* for argument errors, or a
+ *     positive cudaError_t; it never throws, never exits, and never synchronises unless stated
+ *   - egotap_b200_last_error() returns a thread-local description of the last failure
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails
+ */
+#ifndef EGOTAP_B200_H
+#define EGOTAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGOTAP_B200_ABI_VERSION 1
+
+enum { EGOTAP_E_ARG = -1, EGOTAP_E_UNSUPPORTED = -2, EGOTAP_E_DRIVER = -3, EGOTAP_E_STATE = -4 };
+
+/* presets (reference options/dataset_options.py:30-41, utils/util.py:51-52) */
+enum { EGOTAP_PRESET_UNREALEGO = 0, EGOTAP_PRESET_EGOCAP = 1 };
+/* operand precision of the tensor-core contractions (accumulation is always fp32) */
+enum {
+  EGOTAP_PREC_BF16X3 = 0, /* error-compensated bf16 hi/lo split, 3 MMAs: fp32-parity mode */
+  EGOTAP_PREC_BF16 = 1    /* plain bf16 operands, 1 MMA: throughput mode, looser stated bound */
+};
+
+int egotap_b200_abi_version(void);
+const char* egotap_b200_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+long long egotap_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Op level: one tcgen05 GEMM with fused epilogue.  D[g][m][n] = epi(sum_k A[g][m][k]*B[g][n][k]).
+ * Replaces every F.linear / conv-as-GEMM / torch.matmul call site on the path
+ * (reference model/modeling_vit.py:195,226-252,271,326,339; model/network_utils.py:123-142;
+ *  model/custom_cells.py:99,104,107).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct egotap_operand {
+  const void* hi;      /* bf16 [g1][g0][rows][K], K contiguous */
+  const void* lo;      /* bf16 residual x - hi, NULL in EGOTAP_PREC_BF16 */
+  long long ld;        /* row stride, elements */
+  long long rows;      /* rows per group (reads beyond are zero-filled) */
+  long long g0_count, g0_stride, g1_count, g1_stride; /* group dims / strides, elements */
+} egotap_operand;
+
+enum { EGOTAP_ACT_NONE = 0, EGOTAP_ACT_GELU = 1, EGOTAP_ACT_LRELU = 2 };
+enum { EGOTAP_STORE_ROWMAJOR = 0, EGOTAP_STORE_QKV = 1, EGOTAP_STORE_JOINT_REGROUP = 2 };
+
+typedef struct egotap_epilogue {
+  float alpha;            /* v = acc * alpha */
+  const float* scale;     /* v *= scale[n]          (nullable) */
+  const float* bias;      /* v += bias[n]           (nullable) */
+  int act;                /* EGOTAP_ACT_* applied here */
+  const float* resid;     /* v += resid[rrow][col]  (nullable) */
+  long long resid_ld;
+  int resid_mod;          /* rrow = resid_mod ? m % resid_mod : out row */
+  int rows_in, rows_out;  /* out row = g*group_rows + (m/rows_in)*rows_out + m%rows_in  (rows_in==0: m) */
+  long long group_rows;
+  float* out_f32;         /* any subset of the outputs */
+  void* out_hi;           /* bf16 */
+  void* out_lo;           /* bf16 */
+  long long ldo;
+  int col_off;
+  int store;              /* EGOTAP_STORE_* */
+  int qk_cols, tokens;    /* STORE_QKV: cols >= qk_cols go transposed to vt_*[(frame*(N-qk_cols)+c)*tokens+tok] */
+  void* vt_hi;
+  void* vt_lo;
+  int J;                  /* STORE_JOINT_REGROUP */
+} egotap_epilogue;
+
+typedef struct egotap_gemm {
+  egotap_operand a, b;
+  int M, N, K, groups;    /* per-group extents; K % 64 == 0, N % 32 == 0 */
+  int precision;          /* EGOTAP_PREC_* */
+  int variant;            /* -1 = auto; else index into the compiled tile configurations */
+  egotap_epilogue epi;
+} egotap_gemm;
+
+int egotap_b200_gemm(const egotap_gemm* desc, void* stream);
+/* number of compiled tile configurations and a printable name for each */
+int egotap_b200_gemm_num_variants(void);
+const char* egotap_b200_gemm_variant_name(int variant);
+
+/* fp32 -> bf16 hi/lo split of a contiguous array (operand preparation; lo may be NULL) */
+int egotap_b200_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOTAP_B200_H */
