@@ -12,13 +12,15 @@ LIB_PATH = os.path.join(_HERE, "libegotap_b200.so")
 PREC_BF16X3, PREC_BF16 = 0, 1
 PRESET_ID = {"UnrealEgo": 0, "EgoCap": 1}
 ACT_NONE, ACT_GELU, ACT_LRELU = 0, 1, 2
-STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP = 0, 1, 2
+STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP, STORE_HEAD_MERGE = 0, 1, 2, 3
 
 # every symbol include/egotap_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
     "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
     "egotap_b200_split_bf16",
+    "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
+    "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
 ]
 
 
@@ -35,7 +37,7 @@ class Epilogue(C.Structure):
                 ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
                 ("ldo", C.c_longlong), ("col_off", C.c_int), ("store", C.c_int),
                 ("qk_cols", C.c_int), ("tokens", C.c_int), ("vt_hi", C.c_void_p), ("vt_lo", C.c_void_p),
-                ("J", C.c_int)]
+                ("J", C.c_int), ("heads", C.c_int)]
 
 
 class Gemm(C.Structure):
@@ -59,6 +61,13 @@ def lib():
         L.egotap_b200_gemm_variant_name.restype = C.c_char_p
         L.egotap_b200_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
         L.egotap_b200_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.egotap_b200_param_name.restype = C.c_char_p
+        L.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.egotap_b200_plan_destroy.argtypes = [C.c_void_p]
+        L.egotap_b200_pack_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        L.egotap_b200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.egotap_b200_plan_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
         _lib = L
     return _lib
 
@@ -109,7 +118,7 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
         require_cuda(t)
         setattr(e, name, _ptr(t))
     for name in ("act", "resid_ld", "resid_mod", "rows_in", "rows_out", "group_rows", "ldo", "col_off", "store",
-                 "qk_cols", "tokens", "J"):
+                 "qk_cols", "tokens", "J", "heads"):
         setattr(e, name, int(epi.pop(name, 0)))
     if epi:
         raise TypeError("unknown epilogue fields: %s" % sorted(epi))

@@ -18,7 +18,7 @@
 namespace eb {
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
-enum : int { STORE_ROWMAJOR = 0, STORE_QKV = 1, STORE_JOINT_REGROUP = 2 };
+enum : int { STORE_ROWMAJOR = 0, STORE_QKV = 1, STORE_JOINT_REGROUP = 2, STORE_HEAD_MERGE = 3 };
 
 struct EpiParams {
   float alpha;              // v = acc * alpha
@@ -43,6 +43,8 @@ struct EpiParams {
   __nv_bfloat16* vt_lo;
   // STORE_JOINT_REGROUP: m = frame*2J + view*J + j  ->  out row = frame*J + j, column += view*N
   int J;
+  // STORE_HEAD_MERGE: group g = frame*heads + h  ->  out row = frame*tokens + m, column += h*N
+  int heads;
 };
 
 struct GemmShape {
@@ -87,6 +89,9 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int g, int m, int 
     int view = rem / p.J, j = rem % p.J;
     orow = (long long)frame * p.J + j;
     col += view * N;
+  } else if (p.store == STORE_HEAD_MERGE) {
+    orow = (long long)(g / p.heads) * p.tokens + m;
+    col += (g % p.heads) * N;
   } else {
     orow = (p.rows_in > 0) ? (long long)(m / p.rows_in) * p.rows_out + (m % p.rows_in) : (long long)m;
     orow += (long long)g * p.group_rows;

@@ -129,7 +129,7 @@ extern "C" int egotap_b200_gemm(const egotap_gemm* d, void* stream) {
   ep.out_f32 = e.out_f32; ep.out_hi = (__nv_bfloat16*)e.out_hi; ep.out_lo = (__nv_bfloat16*)e.out_lo;
   ep.ldo = e.ldo; ep.col_off = e.col_off; ep.store = e.store;
   ep.qk_cols = e.qk_cols; ep.tokens = e.tokens;
-  ep.vt_hi = (__nv_bfloat16*)e.vt_hi; ep.vt_lo = (__nv_bfloat16*)e.vt_lo; ep.J = e.J;
+  ep.vt_hi = (__nv_bfloat16*)e.vt_hi; ep.vt_lo = (__nv_bfloat16*)e.vt_lo; ep.J = e.J; ep.heads = e.heads;
   EB_REQUIRE(ep.out_f32 || ep.out_hi || (ep.store == STORE_QKV && ep.vt_hi), "gemm: no output pointer");
   EB_REQUIRE(ep.ldo % 8 == 0 && ep.col_off % 32 == 0, "gemm: ldo %% 8 and col_off %% 32 must be 0");
   const int nsplit = d->precision == EGOTAP_PREC_BF16 ? 1 : 3;

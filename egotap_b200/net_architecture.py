@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference's lifting network (same names, arguments and errors).
+
+``EgoTAPAutoEncoder`` here is a drop-in for the reference class of the same name
+(reference ``model/net_architecture.py:579-758``): same constructor signature, same ``opt``
+fields, same ``forward`` / ``predict_pose`` signatures and 4-tuple return, and a ``state_dict``
+with exactly the reference's keys and shapes (117 keys for UnrealEgo,
+115 for EgoCap, including the dead ``cls_token`` / ``pooler`` entries so ``.pth`` files
+round-trip with ``strict=True``).
+
+All arithmetic runs in hand-written sm_100a CUDA behind the C ABI of ``libegotap_b200.so``
+(``include/egotap_b200.h``); this file only owns parameters, packs them for the kernels and
+enqueues the forward pass on the current CUDA stream.  There is no CPU or PyTorch fallback:
+CPU tensors raise ``RuntimeError``.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import capi
+
+_PRESETS = {"UnrealEgo": dict(J=15, parents=16), "EgoCap": dict(J=17, parents=18)}
+HID, EMB, PU_H = 1024, 128, 512
+
+PRECISIONS = {"bf16x3": capi.PREC_BF16X3, "fp32": capi.PREC_BF16X3, "bf16": capi.PREC_BF16}
+
+
+def get_limb_dim(opt):
+    """reference model/net_architecture.py:12-20"""
+    return {"none": 0, "sin": 2, "limb": 1}[opt.heatmap_type]
+
+
+def _state_spec(J, global_head, vit_layers=3):
+    """(key, shape, kind) in the reference's state_dict order.  kind: w (Linear/Conv weight), b (bias),
+    tn (trunc-normal 0.02), zero, one, count."""
+    out = []
+    v = "pos_heatmap_encoder.vit."
+    out += [(v + "embeddings.cls_token", (1, 1, HID), "tn"), (v + "embeddings.mask_token", (1, 1, HID), "zero"),
+            (v + "embeddings.position_embeddings", (1, 576, HID), "tn"),
+            (v + "embeddings.patch_embeddings.projection.weight", (HID, 1, 16, 16), "w"),
+            (v + "embeddings.patch_embeddings.projection.bias", (HID,), "b")]
+    for i in range(vit_layers):
+        lp = v + "encoder.layer.%d." % i
+        for n in ("query", "key", "value"):
+            out += [(lp + "attention.attention.%s.weight" % n, (HID, HID), "w"),
+                    (lp + "attention.attention.%s.bias" % n, (HID,), "b")]
+        out += [(lp + "attention.output.dense.weight", (HID, HID), "w"), (lp + "attention.output.dense.bias", (HID,), "b"),
+                (lp + "intermediate.dense.weight", (4 * HID, HID), "w"), (lp + "intermediate.dense.bias", (4 * HID,), "b"),
+                (lp + "output.dense.weight", (HID, 4 * HID), "w"), (lp + "output.dense.bias", (HID,), "b"),
+                (lp + "layernorm_before.weight", (HID,), "one"), (lp + "layernorm_before.bias", (HID,), "zero"),
+                (lp + "layernorm_after.weight", (HID,), "one"), (lp + "layernorm_after.bias", (HID,), "zero")]
+    out += [(v + "layernorm.weight", (HID,), "one"), (v + "layernorm.bias", (HID,), "zero"),
+            (v + "pooler.dense.weight", (HID, HID), "w"), (v + "pooler.dense.bias", (HID,), "b")]
+    for enc, k1 in (("pos_heatmap_encoder", 16 * HID), ("rot_heatmap_encoder", 2 * 64 * 64)):
+        for name, (n, k) in (("fc1", (2048, k1)), ("fc2", (512, 2048)), ("fc3", (EMB, 512))):
+            p = "%s.%s." % (enc, name)
+            out += [(p + "fc.weight", (n, k), "w"), (p + "fc.bias", (n,), "b"), (p + "bn.weight", (n,), "one"),
+                    (p + "bn.bias", (n,), "zero"), (p + "bn.running_mean", (n,), "buf_zero"),
+                    (p + "bn.running_var", (n,), "buf_one"), (p + "bn.num_batches_tracked", (), "count")]
+    s = "skel_sequential_layer.lstm_custom.layers."
+    X = 2 * EMB
+    for name, (n, k) in (("0.x2f", (PU_H + X, X)), ("0.x2h", (4 * PU_H, X)), ("0.b2h", (4 * PU_H, X)),
+                         ("0.h2h", (4 * PU_H, PU_H)), ("1.x2f", (PU_H, PU_H)), ("1.x2h", (4 * PU_H, PU_H)),
+                         ("1.h2h", (4 * PU_H, PU_H))):
+        out += [(s + name + ".weight", (n, k), "w"), (s + name + ".bias", (n,), "b")]
+    out += [("pose_mlp.pose_fcs.0.weight", (3, X + PU_H), "w"), ("pose_mlp.pose_fcs.0.bias", (3,), "b")]
+    if global_head:
+        out += [("global_mlp.pose_fcs.0.weight", (6, J * PU_H), "w"), ("global_mlp.pose_fcs.0.bias", (6,), "b")]
+    return out
+
+
+class _Node(nn.Module):
+    """Anonymous container so dotted reference keys map onto a real module tree."""
+
+
+def _register(root, key, tensor, is_buffer):
+    parts = key.split(".")
+    m = root
+    for p in parts[:-1]:
+        if p not in m._modules:
+            m.add_module(p, _Node())
+        m = m._modules[p]
+    if is_buffer:
+        m.register_buffer(parts[-1], tensor)
+    else:
+        m.register_parameter(parts[-1], nn.Parameter(tensor))
+
+
+class EgoTAPAutoEncoder(nn.Module):
+    """B200-native drop-in for reference ``EgoTAPAutoEncoder`` (model/net_architecture.py:579-758).
+
+    Extra, optional ``opt`` fields (read with ``getattr`` so the reference's parser needs no change):
+      ``b200_precision``  'bf16x3' (default; fp32-parity mode) or 'bf16' (throughput mode)
+      ``b200_max_batch``  initial workspace batch (grows on demand)
+    """
+
+    def __init__(self, opt, input_channel_scale=1, fc_dim=16384):
+        super().__init__()
+        if opt.joint_preset not in _PRESETS:
+            raise ValueError("joint_preset is {} which is undefined".format(opt.joint_preset))   # reference utils/util.py:66
+        self.joint_preset = opt.joint_preset
+        self.hidden_size = opt.ae_hidden_size
+        self.limb_heatmap_dim = get_limb_dim(opt)
+        self.num_joints = opt.num_heatmap + (1 if opt.estimate_head else 0)
+        self.num_pos_heatmap = opt.num_heatmap
+        self.num_rot_heatmap = opt.num_rot_heatmap
+        assert self.num_pos_heatmap == self.num_rot_heatmap                                         # reference :598
+        self.input_channel_scale = input_channel_scale
+        self.num_heatmap = self.num_pos_heatmap + self.num_rot_heatmap * self.limb_heatmap_dim
+        self.channels_heatmap = self.num_heatmap * input_channel_scale
+        self.W, self.H = opt.load_size_heatmap[0], opt.load_size_heatmap[1]
+        self.pose_dim = self.num_joints * 3
+        self.rot_dim = self.num_rot_heatmap * 3
+        self.use_global_offset = opt.joint_preset == "UnrealEgo" and opt.estimate_head
+        J = _PRESETS[opt.joint_preset]["J"]
+        # The one configuration every reference script uses (scripts/**); anything else is out of scope.
+        unsupported = []
+        if not getattr(opt, "patched_heatmap_ae", False): unsupported.append("patched_heatmap_ae must be set")
+        if getattr(opt, "skel_layer", None) != "PU": unsupported.append("skel_layer must be 'PU'")
+        if getattr(opt, "n_skel_layers", 2) != 2: unsupported.append("n_skel_layers must be 2")
+        if opt.heatmap_type != "sin": unsupported.append("heatmap_type must be 'sin'")
+        if input_channel_scale != 2: unsupported.append("stereo input (input_channel_scale=2) required")
+        if self.hidden_size != EMB: unsupported.append("ae_hidden_size must be 128")
+        if (self.W, self.H) != (64, 64): unsupported.append("load_size_heatmap must be [64, 64]")
+        if self.num_pos_heatmap != J: unsupported.append("num_heatmap must be %d for %s" % (J, opt.joint_preset))
+        if bool(opt.estimate_head) != (opt.joint_preset == "UnrealEgo"):
+            unsupported.append("estimate_head must follow the dataset preset (UnrealEgo: True, EgoCap: False)")
+        if unsupported:
+            raise NotImplementedError("egotap_b200 implements the published EgoTAP configuration only: " + "; ".join(unsupported))
+        self._J = J
+        self._precision = PRECISIONS[str(getattr(opt, "b200_precision", "bf16x3"))]
+        self._max_batch = int(getattr(opt, "b200_max_batch", 0))
+        for key, shape, kind in _state_spec(J, self.use_global_offset):
+            if kind == "count":
+                t = torch.tensor(0, dtype=torch.long)
+            elif kind in ("one", "buf_one"):
+                t = torch.ones(shape)
+            elif kind == "tn":
+                t = torch.empty(shape)
+                nn.init.trunc_normal_(t, mean=0.0, std=0.02)
+            else:
+                t = torch.zeros(shape)
+            _register(self, key, t, is_buffer=kind in ("count", "buf_zero", "buf_one"))
+        self._plan = None
+        self._plan_key = None
+        self._packed_versions = None
+        self._zeros = {}
+        self.skel_inputs = None
+        self.skel_embed = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # ------------------------------------------------------------------ reference-compatible init
+    def init_weights(self, init_type="kaiming", gain=0.02):
+        """reference model/network_utils.py:37-58: every Linear/Conv weight re-initialised, bias 0;
+        BatchNorm1d / LayerNorm / embeddings untouched."""
+        for key, p in self.named_parameters():
+            if p.dim() >= 2 and key.endswith(".weight"):
+                if init_type == "normal":
+                    nn.init.normal_(p.data, 0.0, gain)
+                elif init_type == "xavier":
+                    nn.init.xavier_normal_(p.data.view(p.shape[0], -1), gain=gain)
+                elif init_type == "kaiming":
+                    nn.init.kaiming_normal_(p.data.view(p.shape[0], -1), a=0, mode="fan_in")
+                elif init_type == "orthogonal":
+                    nn.init.orthogonal_(p.data.view(p.shape[0], -1), gain=gain)
+                else:
+                    raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+                bias = dict(self.named_parameters()).get(key[:-len("weight")] + "bias")
+                if bias is not None:
+                    nn.init.constant_(bias.data, 0.0)
+        self._invalidate()
+
+    # ------------------------------------------------------------------ plan / weight cache
+    def _invalidate(self):
+        self._packed_versions = None
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._plan = None
+        self._packed_versions = None
+        self._zeros = {}
+        return r
+
+    def _ensure_plan(self, batch, device):
+        want = max(batch, self._max_batch, 1)
+        key = (device, self._precision)
+        if self._plan is not None and self._plan_key == key and self._plan_batch >= batch:
+            return
+        lib = capi.lib()
+        self._destroy_plan()
+        preset = capi.PRESET_ID[self.joint_preset]
+        pb, wb = C.c_size_t(), C.c_size_t()
+        capi.check(lib.egotap_b200_plan_sizes(preset, self._precision, want, C.byref(pb), C.byref(wb)), "plan_sizes")
+        self._packed = torch.empty(pb.value, dtype=torch.uint8, device=device)
+        self._workspace = torch.empty(wb.value, dtype=torch.uint8, device=device)
+        plan = C.c_void_p()
+        capi.check(lib.egotap_b200_plan_create(preset, self._precision, want, C.c_void_p(self._packed.data_ptr()),
+                                               C.c_void_p(self._workspace.data_ptr()), C.byref(plan)), "plan_create")
+        self._plan, self._plan_key, self._plan_batch = plan, key, want
+        self._packed_versions = None
+
+    def _destroy_plan(self):
+        if getattr(self, "_plan", None) is not None:
+            capi.lib().egotap_b200_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def _param_list(self):
+        lib = capi.lib()
+        preset = capi.PRESET_ID[self.joint_preset]
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        n = lib.egotap_b200_num_params(preset)
+        return [sd[lib.egotap_b200_param_name(preset, i).decode()] for i in range(n)]
+
+    def _ensure_packed(self):
+        tensors = self._param_list()
+        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        if versions == self._packed_versions:
+            return
+        for t in tensors:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("egotap_b200 expects contiguous fp32 parameters (got %s)" % t.dtype)
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        capi.check(capi.lib().egotap_b200_pack_weights(self._plan, arr, len(tensors), capi.current_stream()), "pack_weights")
+        self._packed_versions = versions
+
+    # ------------------------------------------------------------------ forward
+    def _run(self, input, last_stage=-1):
+        if not isinstance(input, torch.Tensor) or not input.is_cuda:
+            raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
+        if self.training:
+            raise NotImplementedError("egotap_b200: the training step (BatchNorm batch statistics + backward) is not "
+                                      "built yet; call .eval() (SURVEY.md section 8(f) row f2)")
+        if next(self.parameters()).device != input.device:
+            raise RuntimeError("egotap_b200: parameters are on %s but input is on %s" % (next(self.parameters()).device, input.device))
+        assert input.dim() == 4 and input.size(1) == self.channels_heatmap and input.size(2) == self.W and input.size(3) == self.H, \
+            "expected (B, %d, %d, %d) heatmaps, got %s" % (self.channels_heatmap, self.W, self.H, tuple(input.shape))
+        x = input.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        B = x.size(0)
+        with torch.cuda.device(x.device):
+            self._ensure_plan(B, x.device)
+            self._ensure_packed()
+            pose = torch.empty((B, self.num_joints, 3), dtype=torch.float32, device=x.device)
+            capi.check(capi.lib().egotap_b200_forward(self._plan, C.c_void_p(x.data_ptr()), B, C.c_void_p(pose.data_ptr()),
+                                                      last_stage, capi.current_stream()), "forward")
+        return pose
+
+    def _zeros_like_reference(self, B, device):
+        key = (B, device)
+        if key not in self._zeros:
+            self._zeros = {key: (torch.zeros((B, self.rot_dim), device=device),
+                                 torch.zeros((B, 3 * 2 * self.num_pos_heatmap), device=device),
+                                 torch.zeros((B, self.channels_heatmap, self.W, self.H), device=device))}
+        return self._zeros[key]
+
+    def predict_pose(self, input, input_rgb_left=None, input_rgb_right=None):
+        return self.forward(input, input_rgb_left, input_rgb_right, pose_only=True)
+
+    def forward(self, input, input_rgb_left=None, input_rgb_right=None, pose_only=False):
+        """heatmaps (B, 6J, 64, 64) -> (pose (B, num_joints, 3), zeros (B, 3J), zeros (B, 6J), zeros like input);
+        RGB arguments are accepted and ignored, as in the reference.  The three auxiliary outputs are
+        all-zero in the reference too (model/net_architecture.py:718-719,756); they are served from a
+        cached buffer instead of a 1.47 MB/frame memset per call -- treat them as read-only."""
+        pose = self._run(input)
+        if pose_only:
+            return pose
+        rot, indep, hm = self._zeros_like_reference(input.size(0), input.device)
+        return pose, rot, indep, hm
+
+    # ------------------------------------------------------------------ parity taps (tests only)
+    def _debug_buffer(self, name, shape, dtype=torch.float32):
+        ptr = C.c_void_p()
+        capi.check(capi.lib().egotap_b200_plan_buffer(self._plan, name.encode(), C.byref(ptr)), "plan_buffer")
+        n = 1
+        for s in shape:
+            n *= s
+        elem = torch.empty((), dtype=dtype).element_size()
+        off = ptr.value - self._workspace.data_ptr()
+        return self._workspace[off:off + n * elem].view(dtype).view(shape)

@@ -54,7 +54,7 @@ typedef struct egotap_operand {
 } egotap_operand;
 
 enum { EGOTAP_ACT_NONE = 0, EGOTAP_ACT_GELU = 1, EGOTAP_ACT_LRELU = 2 };
-enum { EGOTAP_STORE_ROWMAJOR = 0, EGOTAP_STORE_QKV = 1, EGOTAP_STORE_JOINT_REGROUP = 2 };
+enum { EGOTAP_STORE_ROWMAJOR = 0, EGOTAP_STORE_QKV = 1, EGOTAP_STORE_JOINT_REGROUP = 2, EGOTAP_STORE_HEAD_MERGE = 3 };
 
 typedef struct egotap_epilogue {
   float alpha;            /* v = acc * alpha */
@@ -75,7 +75,8 @@ typedef struct egotap_epilogue {
   int qk_cols, tokens;    /* STORE_QKV: cols >= qk_cols go transposed to vt_*[(frame*(N-qk_cols)+c)*tokens+tok] */
   void* vt_hi;
   void* vt_lo;
-  int J;                  /* STORE_JOINT_REGROUP */
+  int J;                  /* STORE_JOINT_REGROUP: m = frame*2J + view*J + j -> row frame*J + j, col += view*N */
+  int heads;              /* STORE_HEAD_MERGE: g = frame*heads + h -> row frame*tokens + m, col += h*N */
 } egotap_epilogue;
 
 typedef struct egotap_gemm {
@@ -93,6 +94,38 @@ const char* egotap_b200_gemm_variant_name(int variant);
 
 /* fp32 -> bf16 hi/lo split of a contiguous array (operand preparation; lo may be NULL) */
 int egotap_b200_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model level: the whole lifting path.  Replaces EgoTAPAutoEncoder.forward
+ * (reference model/net_architecture.py:682-758; called from model/egotap_autoencoder_model.py:223).
+ *
+ *   1. egotap_b200_plan_sizes  -> bytes of the packed-weight buffer and of the workspace for a
+ *      preset / precision / maximum batch; the caller allocates both on the device (torch does)
+ *   2. egotap_b200_plan_create -> lays both buffers out (HBM layout in DESIGN.md)
+ *   3. egotap_b200_pack_weights: fp32 state_dict tensors (device pointers, in the canonical order
+ *      egotap_b200_param_name() enumerates; names are the reference's state_dict keys) ->
+ *      bf16 hi/lo operand matrices, QKV stacked, BN folded, position embeddings permuted to the
+ *      heatmap-major token order.  Re-run after every load_state_dict.
+ *   4. egotap_b200_forward: heatmaps (B, 6J, 64, 64) fp32 -> pose (B, num_joints, 3) fp32, async on stream
+ * ------------------------------------------------------------------------------------------ */
+typedef struct egotap_plan egotap_plan;
+
+int egotap_b200_num_params(int preset);
+const char* egotap_b200_param_name(int preset, int index);
+int egotap_b200_plan_sizes(int preset, int precision, int max_batch, size_t* packed_bytes, size_t* workspace_bytes);
+int egotap_b200_plan_create(int preset, int precision, int max_batch, void* packed, void* workspace, egotap_plan** out);
+int egotap_b200_plan_destroy(egotap_plan* plan);
+int egotap_b200_pack_weights(egotap_plan* plan, const float* const* params, int num_params, void* stream);
+
+/* stages at which egotap_b200_forward can stop (op-level parity taps); -1 or EGOTAP_STAGE_POSE = full path */
+enum {
+  EGOTAP_STAGE_EMBED = 0, EGOTAP_STAGE_LAYER0 = 1, EGOTAP_STAGE_LAYER1 = 2, EGOTAP_STAGE_LAYER2 = 3,
+  EGOTAP_STAGE_VIT_OUT = 4, EGOTAP_STAGE_JOINT_EMBED = 5, EGOTAP_STAGE_LIMB_EMBED = 6, EGOTAP_STAGE_CHAIN = 7,
+  EGOTAP_STAGE_POSE = 8
+};
+int egotap_b200_forward(egotap_plan* plan, const float* heatmaps, int batch, float* pose, int last_stage, void* stream);
+/* device pointer of a named intermediate ("hidden", "fin_hi", "fin_lo", "embed", "h0", "skel") for the parity tests */
+int egotap_b200_plan_buffer(egotap_plan* plan, const char* name, void** ptr);
 
 #ifdef __cplusplus
 }

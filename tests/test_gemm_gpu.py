@@ -1,0 +1,125 @@
+"""Op-level parity: the tcgen05 GEMM and its fused epilogues vs torch (fp64 on the GPU as the checker)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _variants():
+    from egotap_b200 import capi
+    L = capi.lib()
+    return [(v, L.egotap_b200_gemm_variant_name(v).decode()) for v in range(L.egotap_b200_gemm_num_variants())]
+
+
+def _ops(A, B, x3):
+    from egotap_b200 import capi
+    ah, al = capi.split_bf16(A)
+    bh, bl = capi.split_bf16(B)
+    if x3:
+        return ah, al, bh, bl, A.double(), B.double()
+    return ah, None, bh, None, ah.double(), bh.double()
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 768, 128), (1000, 1024, 1024), (77, 128, 512)])
+def test_every_tile_configuration(shape):
+    from egotap_b200 import capi
+    M, N, K = shape
+    torch.manual_seed(1)
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    for v, name in _variants():
+        x3 = "x3" in name
+        ah, al, bh, bl, Ar, Br = _ops(A, B, x3)
+        D = torch.full((M, N), float("nan"), device="cuda")
+        capi.gemm(ah, al, bh, bl, M, N, K, precision=capi.PREC_BF16X3 if x3 else capi.PREC_BF16, variant=v, out_f32=D)
+        ref = Ar @ Br.t()
+        rel = ((D.double() - ref).abs().max() / ref.abs().max()).item()
+        assert rel < (2e-5 if x3 else 3e-6), (name, shape, rel)
+
+
+@pytest.mark.parametrize("x3", [True, False])
+def test_fused_epilogues(x3):
+    from egotap_b200 import capi
+    torch.manual_seed(2)
+    M, N, K = 600, 512, 256
+    prec = capi.PREC_BF16X3 if x3 else capi.PREC_BF16
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.1
+    ah, al, bh, bl, Ar, Br = _ops(A, B, x3)
+    acc = (Ar @ Br.t())
+    bias, scale = torch.randn(N, device="cuda"), torch.rand(N, device="cuda") + 0.5
+    resid = torch.randn(M, N, device="cuda")
+    tol = 3e-5 if x3 else 1e-5
+
+    def close(got, ref, t=tol):
+        assert ((got.double() - ref).abs().max() / ref.abs().max()).item() < t
+
+    # bias + exact GELU -> bf16 hi/lo
+    oh = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); ol = torch.empty_like(oh)
+    capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, bias=bias, act=capi.ACT_GELU, out_hi=oh, out_lo=ol)
+    ref = torch.nn.functional.gelu(acc + bias.double())
+    close(oh.double() + ol.double(), ref, 3e-5)
+    close(oh.double(), ref, 5e-3)                       # hi alone is a bf16 rounding of the result
+    # scale/shift (folded BatchNorm) + LeakyReLU(0.2) -> fp32
+    D = torch.empty(M, N, device="cuda")
+    capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, scale=scale, bias=bias, act=capi.ACT_LRELU, out_f32=D)
+    close(D, torch.nn.functional.leaky_relu(acc * scale.double() + bias.double(), 0.2))
+    # residual, in place
+    D = resid.clone()
+    capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, bias=bias, resid=D, resid_ld=N, out_f32=D)
+    close(D, acc + bias.double() + resid.double())
+    # additive table indexed by m % mod, rows scattered 480 -> 576 per frame (patch-embed epilogue)
+    rows_in, rows_out = 150, 200
+    table = torch.randn(rows_in, N, device="cuda")
+    D = torch.zeros((M // rows_in) * rows_out, N, device="cuda")
+    capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, resid=table, resid_ld=N, resid_mod=rows_in, rows_in=rows_in,
+              rows_out=rows_out, out_f32=D)
+    ref = torch.zeros_like(D, dtype=torch.float64)
+    for f in range(M // rows_in):
+        ref[f * rows_out:f * rows_out + rows_in] = acc[f * rows_in:(f + 1) * rows_in] + table.double()
+    close(D, ref)
+    # alpha
+    D = torch.empty(M, N, device="cuda")
+    capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, alpha=0.125, out_f32=D)
+    close(D, acc * 0.125)
+
+
+def test_qkv_store_and_grouped_attention_shapes():
+    """STORE_QKV (V written transposed per head) feeding the grouped score / context GEMMs == torch attention."""
+    from egotap_b200 import capi
+    torch.manual_seed(3)
+    Bf, T, H, Dh = 3, 576, 8, 128
+    hid = H * Dh
+    x = torch.randn(Bf * T, hid, device="cuda")
+    W = torch.randn(3 * hid, hid, device="cuda") / 32
+    b = torch.randn(3 * hid, device="cuda") * 0.1
+    xh, xl = capi.split_bf16(x); wh, wl = capi.split_bf16(W)
+    qk_h = torch.empty(Bf * T, 2 * hid, device="cuda", dtype=torch.bfloat16); qk_l = torch.empty_like(qk_h)
+    vt_h = torch.empty(Bf * H * Dh, T, device="cuda", dtype=torch.bfloat16); vt_l = torch.empty_like(vt_h)
+    capi.gemm(xh, xl, wh, wl, Bf * T, 3 * hid, hid, bias=b, store=capi.STORE_QKV, qk_cols=2 * hid, tokens=T,
+              out_hi=qk_h, out_lo=qk_l, ldo=2 * hid, vt_hi=vt_h, vt_lo=vt_l)
+    qkv = (x.double() @ W.double().t() + b.double()).view(Bf, T, 3, H, Dh)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    got_qk = (qk_h.double() + qk_l.double()).view(Bf, T, 2, H, Dh)
+    assert (got_qk[:, :, 0].permute(0, 2, 1, 3) - q).abs().max() < 1e-4
+    got_vt = (vt_h.double() + vt_l.double()).view(Bf, H, Dh, T)
+    assert (got_vt - v.transpose(-1, -2)).abs().max() < 1e-4
+    # scores
+    S = torch.empty(Bf * H, T, T, device="cuda")
+    capi.gemm(qk_h, qk_l, qk_h[:, hid:], qk_l[:, hid:], T, T, Dh, groups=Bf * H, lda=2 * hid, ldb=2 * hid,
+              a_group=(H, Dh, Bf, T * 2 * hid), b_group=(H, Dh, Bf, T * 2 * hid), alpha=Dh ** -0.5, out_f32=S, ldo=T,
+              group_rows=T)
+    ref_s = (q @ k.transpose(-1, -2)) * Dh ** -0.5
+    assert ((S.view(Bf, H, T, T).double() - ref_s).abs().max() / ref_s.abs().max()) < 3e-5
+    P = torch.softmax(ref_s, -1).float().contiguous().view(Bf * H * T, T)
+    ph, pl = capi.split_bf16(P)
+    ctx_h = torch.empty(Bf * T, hid, device="cuda", dtype=torch.bfloat16); ctx_l = torch.empty_like(ctx_h)
+    capi.gemm(ph, pl, vt_h, vt_l, T, Dh, T, groups=Bf * H, a_group=(Bf * H, T * T, 1, 0), b_group=(Bf * H, Dh * T, 1, 0),
+              a_rows=T, b_rows=Dh, store=capi.STORE_HEAD_MERGE, heads=H, tokens=T, out_hi=ctx_h, out_lo=ctx_l, ldo=hid)
+    ref_ctx = (torch.softmax(ref_s, -1) @ v).permute(0, 2, 1, 3).reshape(Bf * T, hid)
+    assert ((ctx_h.double() + ctx_l.double() - ref_ctx).abs().max() / ref_ctx.abs().max()) < 3e-5
+
+
+def test_argument_errors_are_reported_not_fatal():
+    from egotap_b200 import capi
+    A = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        capi.gemm(A, A, A, A, 128, 128, 96, out_f32=torch.zeros(128, 128, device="cuda"))
