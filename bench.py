@@ -1,0 +1,264 @@
+"""Benchmark of the EgoTAP heatmap->3D lifting path (BASELINE.json metric: stereo frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl egotap_b200|reference]
+                    [--preset UnrealEgo|EgoCap] [--batch B] [--precision bf16x3|bf16]
+
+A step = one forward pass of the lifting network over one batch of synthetic UnrealEgo-shaped
+heatmaps (default: BASELINE.json configs[1], UnrealEgo preset, batch 256 per GPU, fp32-parity mode).
+N > 1: one process per GPU under torchrun, frames sharded (weak scaling: 256 frames per GPU), the
+only collective is the final gather of the poses.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port in
+oracle/, since the reference is Python and does not travel to the GPU box), bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FLOP_PER_FRAME = {"UnrealEgo": 51.161e9, "EgoCap": 51.600e9}     # BASELINE.md section 2 (algorithmic, 2*MAC)
+METRIC = "stereo_frames_per_sec_heatmap_to_3d"
+CPU_SAMPLE_BATCH = 16                                             # BASELINE.json configs[0]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def time_oracle_cpu(preset, sd, steps, warmup, batch=CPU_SAMPLE_BATCH):
+    """The reference's algorithm (CPU oracle port, fp32, all host threads) on a bounded sample."""
+    import torch
+    import egotap_oracle as orc
+    from egotap_b200.synthetic import synthetic_heatmaps
+    x = synthetic_heatmaps(preset, batch, seed=1234, kind="gauss")
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.forward(sd, x, preset)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pose = orc.forward(sd, x, preset)
+        dt = (time.perf_counter() - t0) / steps
+    return dict(fps=batch / dt, ms_per_step=dt * 1e3, cores=torch.get_num_threads(), batch=batch, pose=pose, x=x)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import weights
+    sd = weights.make_state_dict(args.preset, seed=0, randomize=False)
+    r = time_oracle_cpu(args.preset, sd, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    sample = "%d steps x batch %d frames, fp32, %d host threads" % (args.steps, r["batch"], r["cores"])
+    line = dict(impl="reference", metric=METRIC, value=r["fps"], unit="frames/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=workload_name(args), preset=args.preset, batch_per_step=r["batch"]),
+                cpu_baseline=dict(value=r["fps"], unit="frames/s", cores=r["cores"], kind="port", sample=sample),
+                e2e=dict(value=r["fps"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return "EgoTAP lifting net (3-layer ViT heatmap encoder + limb FC encoder + 2-layer propagation chain + head), " \
+           "%s preset, random-init weights, synthetic stereo joint+limb heatmaps 64x64, batch %d per GPU" % (args.preset, args.batch)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import egotap_b200
+    import egotap_oracle as orc
+    from egotap_b200 import capi
+    from egotap_b200.pipeline import HostPipeline
+    from egotap_b200.sharded import gather_poses
+    from ref_shim import make_opt
+
+    B, K, W = args.batch, args.steps, args.warmup
+    torch.manual_seed(0)                                   # reference-style random init (kaiming), same on every rank
+    net = egotap_b200.EgoTAPAutoEncoder(make_opt(args.preset, b200_precision=args.precision, b200_max_batch=B),
+                                        input_channel_scale=2)
+    net.init_weights("kaiming")
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(dev).eval()
+    x_host = egotap_b200.synthetic_heatmaps(args.preset, B, seed=1234 + rank, kind="gauss").pin_memory()
+    x = x_host.to(dev)
+    total = B * world
+
+    def step():
+        pose = net.predict_pose(x)
+        return gather_poses(pose, total) if world > 1 else pose
+
+    for _ in range(W):
+        pose = step()
+    torch.cuda.synchronize()
+    # ---------------- parity of what is being timed (small sample through the oracle, rank 0)
+    parity = None
+    if rank == 0:
+        with torch.no_grad():
+            ref = orc.forward(sd, x_host[:2], args.preset)
+        parity = orc.parity_report(pose[:2], ref)
+    # ---------------- timed region: inputs resident in HBM
+    launches0 = capi.lib().egotap_b200_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = capi.lib().egotap_b200_launch_count() - launches0
+    # ---------------- end to end: pinned host buffers in, pinned host poses out, copies inside the timed region
+    pipe = HostPipeline(net, B)
+    host_in = [x_host, x_host.clone().pin_memory()]
+    host_out = [torch.empty((B, net.num_joints, 3)).pin_memory() for _ in range(K)]
+    pipe.run([host_in[i % 2] for i in range(min(W, 2))], host_out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    pipe.run([host_in[i % 2] for i in range(K)], host_out)
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    e2e_ok = bool(torch.isfinite(host_out[-1]).all()) and (host_out[-1][:2].to(dev) - pose[:2]).abs().max().item() < 1e-5
+    # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), per-launch CUDA events, one extra step
+    pk = peaks()
+    recs = capi.profile_gemms(lambda: net.predict_pose(x))
+    gemm_ms = sum(r["ms"] for r in recs)
+    gemm_flops = sum(r["flops"] for r in recs)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    nsplit = 3 if args.precision != "bf16" else 1
+    roofline = dict(bound="tensor", kernel="gemm_tc_kernel (all %d launches of one step)" % len(recs), achieved=achieved,
+                    peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"], traffic=None,
+                    peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                    mma_passes_per_flop=nsplit, mma_frac=achieved * nsplit / pk["bf16_sustained"],
+                    gemm_share_of_step=gemm_ms / (ms / K), note="achieved = algorithmic 2*M*N*K over all GEMM launches of one "
+                    "step / their summed CUDA-event durations; bf16x3 issues 3 MMAs per algorithmic FLOP")
+    fps = total * K / (ms * 1e-3)
+    whole = dict(achieved=fps / world * FLOP_PER_FRAME[args.preset] / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s")
+    whole["frac"] = whole["achieved"] / whole["peak"]
+    # ---------------- CPU baseline on this box's host cores (bounded sample)
+    cpu = time_oracle_cpu(args.preset, sd, steps=3, warmup=1)
+    line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16x3 operands, f32 accumulate" if nsplit == 3 else "bf16 operands, f32 accumulate",
+                data="synthetic",
+                config=dict(workload=workload_name(args), preset=args.preset, batch_per_gpu=B, global_batch=total,
+                            precision=args.precision, parallelism="dp%d (frames sharded, final pose gather)" % world,
+                            l2="inputs %.0f MB + activations >> 126 MB L2 per step, no flush needed" % (x.numel() * 4 / 1e6)),
+                e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pipe.h2d_bytes_per_step,
+                         d2h_bytes_per_step=pipe.d2h_bytes_per_step, checked=e2e_ok),
+                gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_whole_step=whole,
+                cpu_baseline=dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
+                                  sample="3 steps x batch %d frames of the same workload, fp32 oracle" % cpu["batch"]),
+                parity=parity)
+    print(json.dumps(line), flush=True)
+    if args.dump:
+        os.makedirs(os.path.dirname(os.path.abspath(args.dump)), exist_ok=True)
+        with open(args.dump, "w") as f:
+            json.dump(dict(line=line, gemm_launches=recs), f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference"])
+    ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1 and "RANK" not in os.environ:
+            raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                             "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP, STORE_HEAD_MERGE = 0, 1, 2, 3
 EXPORTS = [
     "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
     "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
-    "egotap_b200_split_bf16",
+    "egotap_b200_split_bf16", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
     "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
     "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
 ]
@@ -125,3 +125,24 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
     if e.ldo == 0:
         e.ldo = N
     check(lib().egotap_b200_gemm(C.byref(d), current_stream()), "gemm")
+
+
+def profile_gemms(fn):
+    """Run ``fn()`` with per-launch CUDA-event timing of every GEMM; returns a list of dicts
+    (M, N, K, groups, variant, ms, flops = algorithmic 2*M*N*K*groups)."""
+    L = lib()
+    check(L.egotap_b200_profile_begin(), "profile_begin")
+    try:
+        fn()
+    finally:
+        n = C.c_int()
+        check(L.egotap_b200_profile_end(C.byref(n)), "profile_end")
+    out = []
+    M, N, K, G, V, ms = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_float()
+    for i in range(n.value):
+        check(L.egotap_b200_profile_record(i, C.byref(M), C.byref(N), C.byref(K), C.byref(G), C.byref(V), C.byref(ms)),
+              "profile_record")
+        out.append(dict(M=M.value, N=N.value, K=K.value, groups=G.value,
+                        variant=L.egotap_b200_gemm_variant_name(V.value).decode(), ms=ms.value,
+                        flops=2.0 * M.value * N.value * K.value * G.value))
+    return out

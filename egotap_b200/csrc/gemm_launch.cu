@@ -3,7 +3,14 @@
 #include "host_util.cuh"
 #include "internal.h"
 
+#include <vector>
+
 namespace eb {
+
+// Optional per-launch CUDA-event timing of the GEMM launches (bench.py's live roofline measurement).
+struct ProfRec { cudaEvent_t e0, e1; int M, N, K, groups, variant; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
 
 template <int CG, int BN, int NS, int ST>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
@@ -102,12 +109,40 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
   }
   GemmShape sh = s;
   if (sh.gdiv <= 0) sh.gdiv = int(a.g0_count > 0 ? a.g0_count : 1);
-  return v.launch(tm, sh, ep, stream);
+  if (!g_prof_on) return v.launch(tm, sh, ep, stream);
+  ProfRec r{nullptr, nullptr, s.M, s.N, s.K, s.groups, variant};
+  EB_CUDA(cudaEventCreate(&r.e0));
+  EB_CUDA(cudaEventCreate(&r.e1));
+  EB_CUDA(cudaEventRecord(r.e0, stream));
+  rc = v.launch(tm, sh, ep, stream);
+  EB_CUDA(cudaEventRecord(r.e1, stream));
+  g_prof.push_back(r);
+  return rc;
 }
 
 }  // namespace eb
 
 using namespace eb;
+
+extern "C" int egotap_b200_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+extern "C" int egotap_b200_profile_end(int* num_records) {
+  g_prof_on = false;
+  EB_CUDA(cudaDeviceSynchronize());
+  if (num_records) *num_records = int(g_prof.size());
+  return 0;
+}
+extern "C" int egotap_b200_profile_record(int i, int* M, int* N, int* K, int* groups, int* variant, float* ms) {
+  if (i < 0 || i >= int(g_prof.size())) return fail(EGOTAP_E_ARG, "profile_record: index %d out of range", i);
+  const ProfRec& r = g_prof[i];
+  *M = r.M; *N = r.N; *K = r.K; *groups = r.groups; *variant = r.variant;
+  EB_CUDA(cudaEventElapsedTime(ms, r.e0, r.e1));
+  return 0;
+}
 
 extern "C" int egotap_b200_gemm_num_variants(void) { return kNumVariants; }
 extern "C" const char* egotap_b200_gemm_variant_name(int v) {

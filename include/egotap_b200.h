@@ -92,6 +92,12 @@ int egotap_b200_gemm(const egotap_gemm* desc, void* stream);
 int egotap_b200_gemm_num_variants(void);
 const char* egotap_b200_gemm_variant_name(int variant);
 
+/* Per-launch CUDA-event timing of the GEMM launches between begin and end (bench.py's live roofline
+ * measurement; events are recorded on the launching stream).  end() synchronises the device. */
+int egotap_b200_profile_begin(void);
+int egotap_b200_profile_end(int* num_records);
+int egotap_b200_profile_record(int index, int* M, int* N, int* K, int* groups, int* variant, float* ms);
+
 /* fp32 -> bf16 hi/lo split of a contiguous array (operand preparation; lo may be NULL) */
 int egotap_b200_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
 
