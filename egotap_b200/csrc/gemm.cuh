@@ -10,8 +10,9 @@
 // * accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1
 // * the epilogue (bias / scale-shift / GELU / LeakyReLU / residual / re-layout / hi-lo split) is fused
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
-// (warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32), so 4 consecutive warps cover all 128 lanes).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue (4 warps for BN = 128,
+// 8 for BN = 256: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32), so each group of 4 consecutive
+// warps covers all 128 lanes and the two groups split the tile's columns).
 #pragma once
 #include "ptx.cuh"
 
@@ -157,13 +158,15 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+  static constexpr int COLS_PER_EPI_GROUP = BN / (EPI_WARPS / 4);
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 template <int CG, int BN, int NSPLIT, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
@@ -194,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C::EPI_WARPS * CG); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
@@ -278,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
+    const int col_base = ((warp - 2) >> 2) * C::COLS_PER_EPI_GROUP;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int n_blk = tile % nN; const int t2 = tile / nN;
@@ -288,11 +292,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int m = m_blk * C::BM * CG + cta_rank * C::BM + q * 32 + lane;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
+      for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
+        const int n0 = n_blk * BN + col_base + c * 32;
         if (n0 >= s.N) break;
         uint32_t r[32];
-        tmem_ld32(t_addr + c * 32, r);
+        tmem_ld32(t_addr + col_base + c * 32, r);
         tmem_ld_wait();
         if (m < s.M) epi_apply(ep, g, m, n0, s.N, r);
       }
