@@ -18,7 +18,7 @@ STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP, STORE_HEAD_MERGE = 0, 1, 2, 3
 EXPORTS = [
     "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
     "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
-    "egotap_b200_split_bf16", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
+    "egotap_b200_split_bf16", "egotap_b200_attention", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
     "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
     "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
 ]
@@ -61,6 +61,7 @@ def lib():
         L.egotap_b200_gemm_variant_name.restype = C.c_char_p
         L.egotap_b200_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
         L.egotap_b200_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+        L.egotap_b200_attention.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]
         L.egotap_b200_param_name.restype = C.c_char_p
         L.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -103,6 +104,17 @@ def split_bf16(x, want_lo=True):
     return hi, lo
 
 
+def attention(qk_hi, qk_lo, vt_hi, vt_lo, frames, precision=PREC_BF16X3):
+    """Fused attention op: returns (ctx_hi, ctx_lo) bf16 tensors of shape (frames*576, 1024)."""
+    import torch
+    require_cuda(qk_hi, qk_lo, vt_hi, vt_lo)
+    ctx_hi = torch.empty((frames * 576, 1024), dtype=torch.bfloat16, device=qk_hi.device)
+    ctx_lo = torch.empty_like(ctx_hi) if precision == PREC_BF16X3 else None
+    check(lib().egotap_b200_attention(_ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
+                                      frames, precision, current_stream()), "attention")
+    return ctx_hi, ctx_lo
+
+
 def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0), a_rows=None,
          b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
     """Op-level entry used by the tests: D = epi(A @ B^T).  ``epi`` keys mirror ``egotap_epilogue``;
@@ -127,9 +139,9 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
     check(lib().egotap_b200_gemm(C.byref(d), current_stream()), "gemm")
 
 
-def profile_gemms(fn):
-    """Run ``fn()`` with per-launch CUDA-event timing of every GEMM; returns a list of dicts
-    (M, N, K, groups, variant, ms, flops = algorithmic 2*M*N*K*groups)."""
+def profile_kernels(fn):
+    """Run ``fn()`` with per-launch CUDA-event timing of every kernel the library launches; returns a list of
+    dicts (name, ms; GEMMs also M, N, K, groups, variant and flops = algorithmic 2*M*N*K*groups)."""
     L = lib()
     check(L.egotap_b200_profile_begin(), "profile_begin")
     try:
@@ -138,11 +150,19 @@ def profile_gemms(fn):
         n = C.c_int()
         check(L.egotap_b200_profile_end(C.byref(n)), "profile_end")
     out = []
+    name = C.c_char_p()
     M, N, K, G, V, ms = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_float()
     for i in range(n.value):
-        check(L.egotap_b200_profile_record(i, C.byref(M), C.byref(N), C.byref(K), C.byref(G), C.byref(V), C.byref(ms)),
-              "profile_record")
-        out.append(dict(M=M.value, N=N.value, K=K.value, groups=G.value,
-                        variant=L.egotap_b200_gemm_variant_name(V.value).decode(), ms=ms.value,
-                        flops=2.0 * M.value * N.value * K.value * G.value))
+        check(L.egotap_b200_profile_record(i, C.byref(name), C.byref(M), C.byref(N), C.byref(K), C.byref(G), C.byref(V),
+                                           C.byref(ms)), "profile_record")
+        r = dict(name=name.value.decode(), ms=ms.value)
+        if M.value:
+            r.update(M=M.value, N=N.value, K=K.value, groups=G.value,
+                     variant=L.egotap_b200_gemm_variant_name(V.value).decode(),
+                     flops=2.0 * M.value * N.value * K.value * G.value)
+        out.append(r)
     return out
+
+
+def profile_gemms(fn):
+    return [r for r in profile_kernels(fn) if "flops" in r]

@@ -1,0 +1,377 @@
+// Fused multi-head self-attention for the ViT heatmap encoder (576 tokens, 8 heads x 128), sm_100a.
+//   ctx[b, q, h*128 + :] = softmax(Q K^T / sqrt(128)) V        reference model/modeling_vit.py:233-252
+//
+// One persistent CTA per SM walks work items (frame b, head h, 128-row query tile).  Per item the 576 keys
+// are processed in 9 tiles of 64:
+//   warp 0   TMA producer: Q tile once, then K_j / V^T_j tiles through a shared-memory ring
+//   warp 1   MMA issuer:   S_j = Q K_j^T  (tcgen05, fp32 in TMEM, double-buffered),  O += P_j V_j
+//   warps 2-9 softmax:     (two warps per TMEM lane quarter, splitting the 64 keys of a tile)
+//                          tcgen05.ld S_j -> online softmax in the exp2 domain (lazy rescale of O in TMEM only
+//                          when a row maximum grows by more than 2^8) -> P_j as a swizzled K-major bf16 operand
+//                          in shared memory; after the last tile: O / l -> bf16 hi/lo context rows
+// NSPLIT = 3: Q, K, V and P are bf16 hi/lo pairs and every product is 3 MMAs (fp32-parity mode).
+// The score matrix never leaves the SM: HBM traffic is Q, K, V in and ctx out.
+#include "gemm.cuh"
+#include "host_util.cuh"
+#include "internal.h"
+
+namespace eb {
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int AT_TOK = 576, AT_HEADS = 8, AT_D = 128, AT_QT = 128, AT_KT = 64;
+constexpr int AT_NT = AT_TOK / AT_KT;                        // 9 key tiles
+constexpr int AT_QTILES = (AT_TOK + AT_QT - 1) / AT_QT;      // 5 query tiles (the last one is half empty)
+
+template <int NSPLIT>
+struct AttnCfg {
+  static constexpr int NOPS = NSPLIT == 1 ? 1 : 2;
+  static constexpr int Q_BLK = AT_QT * 64 * 2;               // one 64-wide d block of the Q tile (16 KB)
+  static constexpr int Q_BYTES = NOPS * 2 * Q_BLK;
+  static constexpr int K_BLK = AT_KT * 64 * 2;               // one 64-wide d block of a K tile (8 KB)
+  static constexpr int V_BLK = AT_D * 64 * 2;                // V^T tile: 128 d rows x 64 keys (16 KB)
+  static constexpr int SLOT_BYTES = NOPS * V_BLK;            // K tile (2 d blocks) and V^T tile have the same size
+  static constexpr int NSLOTS = NSPLIT == 1 ? 6 : 3;
+  static constexpr int P_BLK = AT_QT * 64 * 2;               // 16 KB
+  static constexpr int P_BYTES = NOPS * P_BLK;                // one P buffer; two are kept (double-buffered)
+  static constexpr int BAR_OFF = Q_BYTES + NSLOTS * SLOT_BYTES + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 2048;     // barriers, pair-exchange floats (base must be 1 KB aligned)
+  static constexpr int TMEM_COLS = 256;                      // S: 2 x 64, O: 128
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(320, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                 const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
+                 const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                 __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items) {
+  using C = AttnCfg<NSPLIT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
+  uint8_t* sQ = smem;
+  uint8_t* sRing = smem + C::Q_BYTES;
+  uint8_t* sP = sRing + C::NSLOTS * C::SLOT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* q_empty = bars + 1;       // [1]
+  uint64_t* kv_full = bars + 2;       // [NSLOTS]
+  uint64_t* kv_empty = kv_full + C::NSLOTS;
+  uint64_t* s_full = kv_empty + C::NSLOTS;  // [2]
+  uint64_t* s_empty = s_full + 2;           // [2]
+  uint64_t* p_full = s_empty + 2;           // [2]
+  uint64_t* pv_done = p_full + 2;           // [2]  PV_j finished: P buffer j%2 free, O up to date
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xchg = reinterpret_cast<float*>(smem + C::BAR_OFF + 256);   // [2][2][128] row maxima (row sums alias buffer 0)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmVh);
+    if (NSPLIT > 1) { tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKl); tma_prefetch_desc(&tmVl); }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base;          // S buffers at columns [0, 128)
+  const uint32_t t_o = tmem_base + 128;    // O at columns [128, 256)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t rc = 0;  // ring counter
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int qt = item % AT_QTILES, bh = item / AT_QTILES;
+        const int h = bh % AT_HEADS, b = bh / AT_HEADS;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, C::Q_BYTES);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_4d(sQ + kb * C::Q_BLK, &tmQh, q_full, kb * 64, qt * AT_QT, h, b);
+          if (NSPLIT > 1) tma_load_4d(sQ + (2 + kb) * C::Q_BLK, &tmQl, q_full, kb * 64, qt * AT_QT, h, b);
+        }
+        // ring order = MMA consumption order: K0, K1, V0, K2, V1, ..., K8, V7, V8
+        for (int step = 0; step < 2 * AT_NT; ++step) {
+          const bool is_k = (step == 0) || (step < 2 * AT_NT - 1 && (step & 1));
+          const int j = (step == 0) ? 0 : (is_k ? (step + 1) / 2 : (step == 2 * AT_NT - 1 ? AT_NT - 1 : step / 2 - 1));
+          const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
+          mbar_wait(&kv_empty[slot], ph ^ 1);
+          uint8_t* dst = sRing + slot * C::SLOT_BYTES;
+          mbar_expect_tx(&kv_full[slot], C::SLOT_BYTES);
+          if (is_k) {
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_load_4d(dst + kb * C::K_BLK, &tmKh, &kv_full[slot], kb * 64, j * AT_KT, AT_HEADS + h, b);
+              if (NSPLIT > 1)
+                tma_load_4d(dst + (2 + kb) * C::K_BLK, &tmKl, &kv_full[slot], kb * 64, j * AT_KT, AT_HEADS + h, b);
+            }
+          } else {
+            tma_load_4d(dst, &tmVh, &kv_full[slot], j * AT_KT, bh * AT_D, 0, 0);
+            if (NSPLIT > 1) tma_load_4d(dst + C::V_BLK, &tmVl, &kv_full[slot], j * AT_KT, bh * AT_D, 0, 0);
+          }
+          ++rc;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_bf16(AT_QT, AT_KT);
+    constexpr uint32_t idesc_o = make_idesc_bf16(AT_QT, AT_D);
+    uint32_t rc = 0, sc = 0, pc = 0;
+    int it = 0;
+    const uint32_t q_lo = sdesc_lo(smem_u32(sQ)), p_lo = sdesc_lo(smem_u32(sP)), ring_addr = smem_u32(sRing);
+    auto issue_s = [&](bool last) {
+      const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
+      const uint32_t sb = sc & 1;
+      mbar_wait(&kv_full[slot], ph);
+      mbar_wait(&s_empty[sb], ((sc >> 1) & 1) ^ 1);
+      tc_fence_after();
+      {
+        const uint32_t k_lo = sdesc_lo(ring_addr + slot * C::SLOT_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t qh = sdesc_at(q_lo, kb * C::Q_BLK + kk * 32);
+            const uint64_t kh = sdesc_at(k_lo, kb * C::K_BLK + kk * 32);
+            umma_bf16<1>(t_s + sb * AT_KT, qh, kh, idesc_s, (kb | kk) != 0 ? 1u : 0u);
+            if (NSPLIT > 1) {
+              const uint64_t ql = sdesc_at(q_lo, (2 + kb) * C::Q_BLK + kk * 32);
+              const uint64_t kl = sdesc_at(k_lo, (2 + kb) * C::K_BLK + kk * 32);
+              umma_bf16<1>(t_s + sb * AT_KT, qh, kl, idesc_s, 1u);
+              umma_bf16<1>(t_s + sb * AT_KT, ql, kh, idesc_s, 1u);
+            }
+          }
+        umma_commit<1>(&kv_empty[slot]);
+        umma_commit<1>(&s_full[sb]);
+        if (last) umma_commit<1>(q_empty);
+      }
+      ++rc; ++sc;
+    };
+    auto issue_pv = [&](bool first) {
+      const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
+      const uint32_t pb = pc & 1;
+      mbar_wait(&kv_full[slot], ph);
+      mbar_wait(&p_full[pb], (pc >> 1) & 1);
+      tc_fence_after();
+      {
+        const uint32_t v_lo = sdesc_lo(ring_addr + slot * C::SLOT_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ph_ = sdesc_at(p_lo, pb * C::P_BYTES + kk * 32);
+          const uint64_t vh = sdesc_at(v_lo, kk * 32);
+          umma_bf16<1>(t_o, ph_, vh, idesc_o, (first && kk == 0) ? 0u : 1u);
+          if (NSPLIT > 1) {
+            const uint64_t pl = sdesc_at(p_lo, pb * C::P_BYTES + C::P_BLK + kk * 32);
+            const uint64_t vl = sdesc_at(v_lo, C::V_BLK + kk * 32);
+            umma_bf16<1>(t_o, ph_, vl, idesc_o, 1u);
+            umma_bf16<1>(t_o, pl, vh, idesc_o, 1u);
+          }
+        }
+        umma_commit<1>(&kv_empty[slot]);
+        umma_commit<1>(&pv_done[pb]);
+      }
+      ++rc; ++pc;
+    };
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      mbar_wait(q_full, it & 1);
+      tc_fence_after();
+      issue_s(false);
+      for (int j = 0; j < AT_NT; ++j) {
+        if (j + 1 < AT_NT) issue_s(j + 1 == AT_NT - 1);
+        issue_pv(j == 0);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warps (8)
+    // Warps w and w+4 own the same TMEM lane quarter (query rows) and split each 64-key tile into two 32-column
+    // halves; the pair agrees on the row maximum through shared memory and a 64-thread named barrier.
+    const int q = warp & 3;                       // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;               // column half handled by this warp
+    const int row = q * 32 + lane;                // query row inside the tile
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    const float c = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
+    uint32_t sc = 0, pc = 0;
+    uint8_t* p_row = sP + row * 128;
+    const int sw = row & 7;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int qt = item % AT_QTILES, bh = item / AT_QTILES;
+      const int h = bh % AT_HEADS, b = bh / AT_HEADS;
+      float m_ref = 0.f, l = 0.f;
+      for (int j = 0; j < AT_NT; ++j) {
+        const uint32_t sb = sc & 1;
+        mbar_wait(&s_full[sb], (sc >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_sel + sb * AT_KT + hf * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        float mt = __uint_as_float(r[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
+        float* xm = xchg + (j & 1) * 256;
+        xm[hf * 128 + row] = mt;
+        pair_sync();
+        mt = fmaxf(mt, xm[(hf ^ 1) * 128 + row]);
+        if (j == 0) m_ref = mt;
+        const bool need = (j > 0) && ((mt - m_ref) * c > 8.0f);
+        // probabilities first (registers only) ...
+        float f = 1.0f;
+        if (need) { f = ex2_approx((m_ref - mt) * c); m_ref = mt; l *= f; }
+        const float mc = m_ref * c;
+        uint32_t hh[16], ll[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), c, -mc));
+          l += p0 + p1;
+          if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+        }
+        // ... then wait until PV_{j-2} has completed (this P buffer is free); only a rescale of O additionally
+        // needs PV_{j-1}
+        const uint32_t pb = pc & 1;
+        mbar_wait(&pv_done[pb], ((pc >> 1) & 1) ^ 1);
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[pb ^ 1], (((pc - 1) >> 1) & 1));
+          tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t o[32];
+            tmem_ld32(t_o + lane_sel + hf * 64 + ch * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(t_o + lane_sel + hf * 64 + ch * 32, o);
+          }
+          tmem_st_wait();
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int off = pb * C::P_BYTES + ((hf * 4 + cc) ^ sw) * 16;   // 128-byte swizzle: chunk index ^ (row % 8)
+          *reinterpret_cast<uint4*>(p_row + off) = make_uint4(hh[4 * cc], hh[4 * cc + 1], hh[4 * cc + 2], hh[4 * cc + 3]);
+          if (NSPLIT > 1)
+            *reinterpret_cast<uint4*>(p_row + C::P_BLK + off) = make_uint4(ll[4 * cc], ll[4 * cc + 1], ll[4 * cc + 2], ll[4 * cc + 3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
+        ++sc; ++pc;
+      }
+      // ---- epilogue: O / l -> ctx rows (each warp of the pair stores its 64 of the 128 head columns)
+      float* xl = xchg;            // tile 8 used buffer 0 last and both warps are past its barrier
+      pair_sync();
+      xl[hf * 128 + row] = l;
+      pair_sync();
+      l += xl[(hf ^ 1) * 128 + row];
+      mbar_wait(&pv_done[(pc - 1) & 1], ((pc - 1) >> 1) & 1);   // last PV of the item
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const int tok = qt * AT_QT + row;
+      const long long orow = (long long)b * AT_TOK + tok;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(t_o + lane_sel + hf * 64 + ch * 32, o);
+        tmem_ld_wait();
+        if (tok < AT_TOK) {
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float v0 = __uint_as_float(o[2 * e]) * inv, v1 = __uint_as_float(o[2 * e + 1]) * inv;
+            if (NSPLIT > 1) split_pack2(v0, v1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(v0, v1);
+          }
+          const long long off = orow * (AT_HEADS * AT_D) + h * AT_D + hf * 64 + ch * 32;
+          uint4* oh = reinterpret_cast<uint4*>(ctx_hi + off);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = make_uint4(hh[4 * e], hh[4 * e + 1], hh[4 * e + 2], hh[4 * e + 3]);
+          if (NSPLIT > 1) {
+            uint4* ol = reinterpret_cast<uint4*>(ctx_lo + off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ol[e] = make_uint4(ll[4 * e], ll[4 * e + 1], ll[4 * e + 2], ll[4 * e + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      pair_sync();   // the partner has consumed xl before the next item's exchange reuses it
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+}
+
+template <int NSPLIT>
+static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B,
+                            cudaStream_t stream) {
+  using C = AttnCfg<NSPLIT>;
+  auto kern = attention_kernel<NSPLIT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int items = B * AT_HEADS * AT_QTILES;
+  const int grid = items < num_sms() ? items : num_sms();
+  ProfScope prof("attention_kernel", stream);
+  kern<<<grid, 320, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ctx_hi, ctx_lo, items);
+  EB_CHECK_LAUNCH("attention_kernel");
+  return 0;
+}
+
+// qk: (B*576, 2048) = [Q | K] per token, head h at columns h*128; vt: (B*8*128, 576) = V^T per (frame, head)
+int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
+                  const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
+                  cudaStream_t stream) {
+  EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");
+  EB_REQUIRE(nsplit == 1 || (qk_lo && vt_lo && ctx_lo), "attention: bf16x3 mode needs the lo parts");
+  CUtensorMap tm[6];
+  int rc;
+  const long long fs = (long long)AT_TOK * 2 * AT_HEADS * AT_D;  // frame stride of the qk buffer
+  for (int part = 0; part < (nsplit == 3 ? 2 : 1); ++part) {
+    const __nv_bfloat16* qk = part == 0 ? qk_hi : qk_lo;
+    const __nv_bfloat16* vt = part == 0 ? vt_hi : vt_lo;
+    if ((rc = make_operand_tmap(&tm[0 + part], qk, AT_D, AT_TOK, 2 * AT_HEADS * AT_D, 2 * AT_HEADS, AT_D, B, fs, AT_QT)))
+      return rc;
+    if ((rc = make_operand_tmap(&tm[2 + part], qk, AT_D, AT_TOK, 2 * AT_HEADS * AT_D, 2 * AT_HEADS, AT_D, B, fs, AT_KT)))
+      return rc;
+    if ((rc = make_operand_tmap(&tm[4 + part], vt, AT_TOK, (long long)B * AT_HEADS * AT_D, AT_TOK, 1, 0, 1, 0, AT_D)))
+      return rc;
+  }
+  if (nsplit == 1) { tm[1] = tm[0]; tm[3] = tm[2]; tm[5] = tm[4]; }
+  return nsplit == 3 ? launch_attention<3>(tm, ctx_hi, ctx_lo, B, stream)
+                     : launch_attention<1>(tm, ctx_hi, ctx_lo, B, stream);
+}
+
+}  // namespace eb
+
+extern "C" int egotap_b200_attention(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo,
+                                     void* ctx_hi, void* ctx_lo, int frames, int precision, void* stream) {
+  return eb::attention_run((const __nv_bfloat16*)qk_hi, (const __nv_bfloat16*)qk_lo, (const __nv_bfloat16*)vt_hi,
+                           (const __nv_bfloat16*)vt_lo, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo, frames,
+                           precision == EGOTAP_PREC_BF16 ? 1 : 3, (cudaStream_t)stream);
+}

@@ -7,11 +7,6 @@
 
 namespace eb {
 
-// Optional per-launch CUDA-event timing of the GEMM launches (bench.py's live roofline measurement).
-struct ProfRec { cudaEvent_t e0, e1; int M, N, K, groups, variant; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
-
 template <int CG, int BN, int NS, int ST>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
   using C = GemmCfg<CG, BN, NS, ST>;
@@ -109,40 +104,13 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
   }
   GemmShape sh = s;
   if (sh.gdiv <= 0) sh.gdiv = int(a.g0_count > 0 ? a.g0_count : 1);
-  if (!g_prof_on) return v.launch(tm, sh, ep, stream);
-  ProfRec r{nullptr, nullptr, s.M, s.N, s.K, s.groups, variant};
-  EB_CUDA(cudaEventCreate(&r.e0));
-  EB_CUDA(cudaEventCreate(&r.e1));
-  EB_CUDA(cudaEventRecord(r.e0, stream));
-  rc = v.launch(tm, sh, ep, stream);
-  EB_CUDA(cudaEventRecord(r.e1, stream));
-  g_prof.push_back(r);
-  return rc;
+  ProfScope prof("gemm_tc_kernel", stream, s.M, s.N, s.K, s.groups, variant);
+  return v.launch(tm, sh, ep, stream);
 }
 
 }  // namespace eb
 
 using namespace eb;
-
-extern "C" int egotap_b200_profile_begin(void) {
-  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
-  g_prof.clear();
-  g_prof_on = true;
-  return 0;
-}
-extern "C" int egotap_b200_profile_end(int* num_records) {
-  g_prof_on = false;
-  EB_CUDA(cudaDeviceSynchronize());
-  if (num_records) *num_records = int(g_prof.size());
-  return 0;
-}
-extern "C" int egotap_b200_profile_record(int i, int* M, int* N, int* K, int* groups, int* variant, float* ms) {
-  if (i < 0 || i >= int(g_prof.size())) return fail(EGOTAP_E_ARG, "profile_record: index %d out of range", i);
-  const ProfRec& r = g_prof[i];
-  *M = r.M; *N = r.N; *K = r.K; *groups = r.groups; *variant = r.variant;
-  EB_CUDA(cudaEventElapsedTime(ms, r.e0, r.e1));
-  return 0;
-}
 
 extern "C" int egotap_b200_gemm_num_variants(void) { return kNumVariants; }
 extern "C" const char* egotap_b200_gemm_variant_name(int v) {
@@ -155,7 +123,7 @@ extern "C" int egotap_b200_gemm(const egotap_gemm* d, void* stream) {
                 d->a.g0_count, d->a.g0_stride, d->a.g1_count, d->a.g1_stride};
   GemmOperand b{(const __nv_bfloat16*)d->b.hi, (const __nv_bfloat16*)d->b.lo, d->b.ld, d->b.rows,
                 d->b.g0_count, d->b.g0_stride, d->b.g1_count, d->b.g1_stride};
-  GemmShape s{d->M, d->N, d->K, d->groups, 0};
+  GemmShape s{d->M, d->N, d->K, d->groups, 0, 0};
   const egotap_epilogue& e = d->epi;
   EpiParams ep;
   ep.alpha = e.alpha; ep.scale = e.scale; ep.bias = e.bias; ep.act = e.act;

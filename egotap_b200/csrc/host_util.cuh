@@ -47,6 +47,34 @@ inline std::atomic<long long>& launch_counter() {
     if (!(cond)) return eb::fail(EGOTAP_E_ARG, __VA_ARGS__);    \
   } while (0)
 
+// Optional per-launch CUDA-event timing (egotap_b200_profile_*): a ProfScope around a launch records start/end
+// events on the launching stream while profiling is on, and costs one branch otherwise.
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  const char* name;
+  int M, N, K, groups, variant;
+};
+bool& prof_on();
+void prof_push(const ProfRec& r);
+struct ProfScope {
+  ProfRec r;
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* name, cudaStream_t stream, int M = 0, int N = 0, int K = 0, int groups = 0, int variant = -1)
+      : st(stream), on(prof_on()) {
+    if (!on) return;
+    r = ProfRec{nullptr, nullptr, name, M, N, K, groups, variant};
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    prof_push(r);
+  }
+};
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

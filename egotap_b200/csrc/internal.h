@@ -20,6 +20,11 @@ int pick_variant(int M, int N, int groups, int nsplit);
 int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, const EpiParams& ep, int nsplit,
              int variant, cudaStream_t stream);
 
+// attention.cu
+int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
+                  const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
+                  cudaStream_t stream);
+
 // kernels.cu
 int split_bf16_run(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t stream);
 

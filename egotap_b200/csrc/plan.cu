@@ -31,6 +31,8 @@ int pos_permute_run(const float*, const float*, int, int, float*, float*, cudaSt
 constexpr int HID = 1024, HEADS = 8, HDIM = 128, TOK = 576, MLP = 4096, EMB = 128, PUH = 512, PUX = 256;
 constexpr int NLAYERS = 3;
 
+static bool fused_attention();
+
 struct W2 {  // bf16 hi/lo weight matrix [N][K]
   __nv_bfloat16* hi = nullptr;
   __nv_bfloat16* lo = nullptr;
@@ -92,7 +94,7 @@ static std::vector<std::string> param_names(int preset) {
 struct Plan {
   int preset, precision, nsplit, max_batch;
   int J, n_hm, grid, live, nj;
-  bool global_head, packed_ok = false;
+  bool global_head, packed_ok = false, fused_attention_layout = true;
   std::vector<std::string> names;
   // ---- packed weights
   W2 w_patch;
@@ -172,8 +174,13 @@ struct Plan {
     ln = take2(w, B * TOK * HID);
     qk = take2(w, B * TOK * 2 * HID);
     vt = take2(w, B * TOK * HID);
-    S = w.take<float>(B * HEADS * TOK * TOK);
-    P = take2(w, B * HEADS * TOK * TOK);
+    if (!fused_attention_layout) {  // score / probability scratch of the unfused A/B path only
+      S = w.take<float>(B * HEADS * TOK * TOK);
+      P = take2(w, B * HEADS * TOK * TOK);
+    } else {
+      S = nullptr;
+      P = W2();
+    }
     ctx = take2(w, B * TOK * HID);
     mlp = take2(w, B * TOK * MLP);
     fin = take2(w, B * n_hm * 16 * HID);
@@ -209,7 +216,28 @@ static int plan_init(Plan& pl, int preset, int precision, int max_batch) {
   pl.grid = 6;  // int(sqrt(n_hm - 1)) + 1 for n_hm = 30 and 34 (reference model/net_architecture.py:328)
   pl.live = pl.n_hm * 16;
   pl.names = param_names(preset);
+  pl.fused_attention_layout = fused_attention();
   return 0;
+}
+
+// EGOTAP_ATTN=unfused selects the three-kernel attention (score GEMM, softmax, context GEMM) kept for A/B checks
+static bool fused_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EGOTAP_ATTN");
+    v = (e && std::string(e) == "unfused") ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// EGOTAP_SKIP_DUMMY=0 computes the last layer's dummy-token rows too (A/B check; results are identical)
+static bool skip_dummy_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EGOTAP_SKIP_DUMMY");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static GemmOperand opnd(const W2& w, long long ld, long long rows) { return GemmOperand{w.hi, w.lo, ld, rows, 1, 0, 1, 0}; }
@@ -224,8 +252,19 @@ static EpiParams epi0() {
 // y = epi(A[M,K] . W[N,K]^T) for plain (ungrouped) operands
 static int linear(const Plan& pl, const W2& a, long long lda, int M, int K, const W2& w, int N, const EpiParams& e,
                   cudaStream_t st) {
-  GemmShape s{M, N, K, 1, 1};
+  GemmShape s{M, N, K, 1, 1, 0};
   return gemm_run(opnd(a, lda, M), opnd(w, K, N), s, e, pl.nsplit, -1, st);
+}
+
+// Same, but only over the first `live` of every frame's 576 token rows (the dummy/mask tokens of the last layer
+// are attended to as keys/values but their own rows are never read again: SURVEY 0.7).  One group per frame.
+static int linear_live(const Plan& pl, const W2& a, long long lda, int B, int live, int K, const W2& w, int N,
+                       EpiParams e, cudaStream_t st) {
+  GemmOperand A{a.hi, a.lo, lda, live, B, (long long)TOK * lda, 1, 0};
+  GemmOperand Wt{w.hi, w.lo, K, N, 1, 0, 1, 0};      // weights: every group multiplies the same matrix
+  e.group_rows = TOK;
+  GemmShape s{live, N, K, B, B, 1};
+  return gemm_run(A, Wt, s, e, pl.nsplit, -1, st);
 }
 
 static int pack(Plan& pl, const float* const* P, int n, cudaStream_t st) {
@@ -327,41 +366,51 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
       e.vt_hi = pl.vt.hi; e.vt_lo = pl.vt.lo;
       RC(linear(pl, pl.ln, HID, M, HID, L.qkv, 3 * HID, e, st));
     }
-    {  // K6a: scores S[b,h] = Q K^T / sqrt(128)
-      EpiParams e = epi0();
-      e.alpha = 0.08838834764831845f;
-      e.out_f32 = pl.S; e.ldo = TOK; e.group_rows = TOK;
-      GemmOperand q{pl.qk.hi, pl.qk.lo, 2 * HID, TOK, HEADS, HDIM, B, (long long)TOK * 2 * HID};
-      GemmOperand k{pl.qk.hi + HID, pl.qk.lo ? pl.qk.lo + HID : nullptr, 2 * HID, TOK, HEADS, HDIM, B,
-                    (long long)TOK * 2 * HID};
-      GemmShape s{TOK, TOK, HDIM, B * HEADS, HEADS};
-      RC(gemm_run(q, k, s, e, pl.nsplit, -1, st));
+    if (fused_attention()) {
+      // K6: fused softmax attention, scores stay in TMEM / shared memory
+      RC(attention_run(pl.qk.hi, pl.qk.lo, pl.vt.hi, pl.vt.lo, pl.ctx.hi, pl.ctx.lo, B, pl.nsplit, st));
+    } else {
+      {  // K6a: scores S[b,h] = Q K^T / sqrt(128)
+        EpiParams e = epi0();
+        e.alpha = 0.08838834764831845f;
+        e.out_f32 = pl.S; e.ldo = TOK; e.group_rows = TOK;
+        GemmOperand q{pl.qk.hi, pl.qk.lo, 2 * HID, TOK, HEADS, HDIM, B, (long long)TOK * 2 * HID};
+        GemmOperand k{pl.qk.hi + HID, pl.qk.lo ? pl.qk.lo + HID : nullptr, 2 * HID, TOK, HEADS, HDIM, B,
+                      (long long)TOK * 2 * HID};
+        GemmShape s{TOK, TOK, HDIM, B * HEADS, HEADS, 0};
+        RC(gemm_run(q, k, s, e, pl.nsplit, -1, st));
+      }
+      RC(softmax_run(pl.S, (long long)B * HEADS * TOK, TOK, pl.P.hi, pl.P.lo, st));
+      {  // K6b: context = P V, heads merged back to (B*576, 1024)
+        EpiParams e = epi0();
+        e.store = STORE_HEAD_MERGE; e.heads = HEADS; e.tokens = TOK;
+        e.out_hi = pl.ctx.hi; e.out_lo = pl.ctx.lo; e.ldo = HID;
+        GemmOperand p{pl.P.hi, pl.P.lo, TOK, TOK, (long long)B * HEADS, (long long)TOK * TOK, 1, 0};
+        GemmOperand v{pl.vt.hi, pl.vt.lo, TOK, HDIM, (long long)B * HEADS, (long long)HDIM * TOK, 1, 0};
+        GemmShape s{TOK, HDIM, TOK, B * HEADS, B * HEADS, 0};
+        RC(gemm_run(p, v, s, e, pl.nsplit, -1, st));
+      }
     }
-    RC(softmax_run(pl.S, (long long)B * HEADS * TOK, TOK, pl.P.hi, pl.P.lo, st));
-    {  // K6b: context = P V, heads merged back to (B*576, 1024)
-      EpiParams e = epi0();
-      e.store = STORE_HEAD_MERGE; e.heads = HEADS; e.tokens = TOK;
-      e.out_hi = pl.ctx.hi; e.out_lo = pl.ctx.lo; e.ldo = HID;
-      GemmOperand p{pl.P.hi, pl.P.lo, TOK, TOK, (long long)B * HEADS, (long long)TOK * TOK, 1, 0};
-      GemmOperand v{pl.vt.hi, pl.vt.lo, TOK, HDIM, (long long)B * HEADS, (long long)HDIM * TOK, 1, 0};
-      GemmShape s{TOK, HDIM, TOK, B * HEADS, B * HEADS};
-      RC(gemm_run(p, v, s, e, pl.nsplit, -1, st));
-    }
+    // worthwhile only when the per-frame tiling of the live rows issues fewer MMA rows than the dense tiling
+    const bool last = (l == NLAYERS - 1) && skip_dummy_rows() && ((live + 255) / 256) * 256 < TOK;
     {  // K7: output projection + residual (in place on the fp32 residual stream)
       EpiParams e = epi0();
       e.bias = L.b_o; e.resid = pl.hidden; e.resid_ld = HID; e.out_f32 = pl.hidden; e.ldo = HID;
-      RC(linear(pl, pl.ctx, HID, M, HID, L.o, HID, e, st));
+      if (last) RC(linear_live(pl, pl.ctx, HID, B, live, HID, L.o, HID, e, st));
+      else RC(linear(pl, pl.ctx, HID, M, HID, L.o, HID, e, st));
     }
     RC(layernorm_run(pl.hidden, L.ln2w, L.ln2b, B, TOK, TOK, 1e-12f, pl.ln.hi, pl.ln.lo, nullptr, st));
     {  // K8: MLP up + exact GELU
       EpiParams e = epi0();
       e.bias = L.b_up; e.act = ACT_GELU; e.out_hi = pl.mlp.hi; e.out_lo = pl.mlp.lo; e.ldo = MLP;
-      RC(linear(pl, pl.ln, HID, M, HID, L.up, MLP, e, st));
+      if (last) RC(linear_live(pl, pl.ln, HID, B, live, HID, L.up, MLP, e, st));
+      else RC(linear(pl, pl.ln, HID, M, HID, L.up, MLP, e, st));
     }
     {  // K9: MLP down + residual
       EpiParams e = epi0();
       e.bias = L.b_down; e.resid = pl.hidden; e.resid_ld = HID; e.out_f32 = pl.hidden; e.ldo = HID;
-      RC(linear(pl, pl.mlp, MLP, M, MLP, L.down, HID, e, st));
+      if (last) RC(linear_live(pl, pl.mlp, MLP, B, live, MLP, L.down, HID, e, st));
+      else RC(linear(pl, pl.mlp, MLP, M, MLP, L.down, HID, e, st));
     }
     if (last_stage == ST_LAYER0 + l) return 0;
   }

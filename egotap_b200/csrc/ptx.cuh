@@ -162,35 +162,51 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   return d;
 }
 
+// Cheap per-MMA descriptor arithmetic: the high word of a 128B-swizzle K-major descriptor (SBO = 1024, version 1,
+// swizzle mode 2) is the constant 0x40004040; the low word is (address >> 4) | (LBO >> 4) << 16, so advancing
+// inside a tile is one 32-bit add of (byte offset >> 4).  Shared memory is < 256 KB, so the 14-bit field never carries.
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t sdesc_at(uint32_t base_lo, uint32_t byte_off) {
+  return (uint64_t(0x40004040u) << 32) | uint64_t(base_lo + (byte_off >> 4));
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: MMA, commit, TMEM load
 // ---------------------------------------------------------------------------------------------
+// Both wrappers are called by ALL lanes of the (converged) MMA warp and elect one lane inside the asm block:
+// keeping the surrounding address arithmetic in warp-uniform control flow lets ptxas build the descriptors in
+// uniform registers instead of per-MMA R2UR "waterfall" loops (measured: ~100 -> ~20 issue cycles per MMA).
+// elect.sync with a full mask always elects the same lane, so MMAs and their commits come from one thread.
 template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   if constexpr (CG == 1)
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   else
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
+// Arrive on an mbarrier once all previously issued MMAs of the elected thread have completed.
 // CG == 2: the arrive is multicast to the barrier at the same offset in both CTAs of the pair.
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   if constexpr (CG == 1)
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
   else
     asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
         ::"r"(smem_u32(bar)), "h"((uint16_t)3)
         : "memory");
 }
@@ -218,6 +234,27 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+}
+// two floats -> packed bf16x2 (x0 in the low half), round to nearest even: one F2FP instruction
+__device__ __forceinline__ uint32_t cvt_bf16x2(float x0, float x1) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
+  return d;
+}
+// packed hi/lo split of two floats: 6 instructions per pair
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_bf16x2(x0, x1);
+  lo = cvt_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, 2 ulp
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace eb

@@ -92,11 +92,19 @@ int egotap_b200_gemm(const egotap_gemm* desc, void* stream);
 int egotap_b200_gemm_num_variants(void);
 const char* egotap_b200_gemm_variant_name(int variant);
 
-/* Per-launch CUDA-event timing of the GEMM launches between begin and end (bench.py's live roofline
- * measurement; events are recorded on the launching stream).  end() synchronises the device. */
+/* Op level: fused multi-head self-attention over 576 tokens, 8 heads x 128 (reference
+ * model/modeling_vit.py:233-252).  qk: (frames*576, 2048) bf16 = [Q | K] per token, head h at columns h*128;
+ * vt: (frames*8*128, 576) bf16 = V transposed per (frame, head) -- both as written by the QKV GEMM's
+ * EGOTAP_STORE_QKV epilogue; ctx: (frames*576, 1024) bf16.  lo parts NULL in EGOTAP_PREC_BF16. */
+int egotap_b200_attention(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, void* ctx_hi,
+                          void* ctx_lo, int frames, int precision, void* stream);
+
+/* Per-launch CUDA-event timing of every kernel launched between begin and end (bench.py's live roofline
+ * measurement; events are recorded on the launching stream).  end() synchronises the device.  GEMM records
+ * carry their shape; other kernels report M = N = K = 0. */
 int egotap_b200_profile_begin(void);
 int egotap_b200_profile_end(int* num_records);
-int egotap_b200_profile_record(int index, int* M, int* N, int* K, int* groups, int* variant, float* ms);
+int egotap_b200_profile_record(int index, const char** name, int* M, int* N, int* K, int* groups, int* variant, float* ms);
 
 /* fp32 -> bf16 hi/lo split of a contiguous array (operand preparation; lo may be NULL) */
 int egotap_b200_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python bench.py --steps 20 --warmup 3 --dump gpurun_out/bench_x3.json 2>&1 | tail -1 | cut -c1-300
+timeout 600 python bench.py --steps 20 --warmup 3 --precision bf16 --dump gpurun_out/bench_bf16.json 2>&1 | tail -1 | cut -c1-300
+python tools/summarize_bench.py gpurun_out/bench_x3.json
+python tools/summarize_bench.py gpurun_out/bench_bf16.json
