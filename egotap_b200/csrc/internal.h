@@ -25,6 +25,13 @@ int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const 
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
                   cudaStream_t stream);
 
+// pu_chain.cu
+int pu_permute_split_run(const float* W, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);
+int pu_chain_run(const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, const float* G, long long G_rs, long long G_ts,
+                 const float* F, long long F_rs, long long F_ts, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                 __nv_bfloat16* hg_hi, __nv_bfloat16* hg_lo, unsigned int* counters, int B, int J, int nsplit,
+                 cudaStream_t stream);
+
 // kernels.cu
 int split_bf16_run(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long n, cudaStream_t stream);
 

@@ -109,13 +109,14 @@ struct Plan {
     float *scale, *shift;
     int n, k;
   } pfc[3], rfc[3];
-  W2 x2f0, xb0, hh0, cat1, hh1;
+  W2 x2f0, xb0, hh0, cat1, hh1, hh0p, hh1p;   // hh*p: gate-permuted copies for the persistent chain kernel
   float *b_x2f0, *b_g0, *b_cat1;
   float *Wp, *bp, *Wg, *bg;
   size_t packed_bytes;
   // ---- workspace
   W2 a_patch, a_limb, ln, qk, vt, P, ctx, mlp, fin, f1, f2, xb, hg, h0b;
   float *hidden, *S, *E, *F0, *G0, *gates, *cst, *H0, *FG1, *skel;
+  unsigned int* counters;
   size_t workspace_bytes;
 
   W2 take2(Bump& b, size_t n) {
@@ -159,6 +160,8 @@ struct Plan {
     hh0 = take2(p, size_t(4 * PUH) * PUH);
     cat1 = take2(p, size_t(5 * PUH) * PUH);
     hh1 = take2(p, size_t(4 * PUH) * PUH);
+    hh0p = take2(p, size_t(4 * PUH) * PUH);
+    hh1p = take2(p, size_t(4 * PUH) * PUH);
     b_x2f0 = p.take<float>(PUH + PUX);
     b_g0 = p.take<float>(4 * PUH);
     b_cat1 = p.take<float>(5 * PUH);
@@ -192,7 +195,8 @@ struct Plan {
     G0 = w.take<float>(B * J * 4 * PUH);
     gates = w.take<float>(B * 4 * PUH);
     cst = w.take<float>(B * PUH);
-    hg = take2(w, B * PUH);
+    hg = take2(w, 2 * B * PUH);
+    counters = w.take<unsigned int>(64);
     H0 = w.take<float>(B * J * PUH);
     h0b = take2(w, B * J * PUH);
     FG1 = w.take<float>(B * J * 5 * PUH);
@@ -236,6 +240,16 @@ static bool skip_dummy_rows() {
   if (v < 0) {
     const char* e = getenv("EGOTAP_SKIP_DUMMY");
     v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// EGOTAP_PU=steps selects the per-joint launch sequence (h2h GEMM + cell kernel per step) kept for A/B checks
+static bool persistent_chain() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EGOTAP_PU");
+    v = (e && std::string(e) == "steps") ? 0 : 1;
   }
   return v == 1;
 }
@@ -313,6 +327,7 @@ static int pack(Plan& pl, const float* const* P, int n, cudaStream_t st) {
   RC(split2d_run(b2h0, 4 * PUH, PUX, PUX, pl.xb0.hi + PUX, pl.xb0.lo ? pl.xb0.lo + PUX : nullptr, 2 * PUX, st));
   RC(vec_add3_run(bx2h0, bb2h0, bh2h0, pl.b_g0, 4 * PUH, st));
   RC(split2d_run(h2h0, 4 * PUH, PUH, PUH, pl.hh0.hi, pl.hh0.lo, PUH, st));
+  RC(pu_permute_split_run(h2h0, pl.hh0p.hi, pl.hh0p.lo, st));
   // layer-1 x-side: N-concatenated [x2f ; x2h]
   RC(split2d_run(x2f1, PUH, PUH, PUH, pl.cat1.hi, pl.cat1.lo, PUH, st));
   RC(split2d_run(x2h1, 4 * PUH, PUH, PUH, pl.cat1.hi + size_t(PUH) * PUH,
@@ -320,6 +335,7 @@ static int pack(Plan& pl, const float* const* P, int n, cudaStream_t st) {
   COPYF(pl.b_cat1, bx2f1, PUH);
   RC(vec_add3_run(bx2h1, bh2h1, nullptr, pl.b_cat1 + PUH, 4 * PUH, st));
   RC(split2d_run(h2h1, 4 * PUH, PUH, PUH, pl.hh1.hi, pl.hh1.lo, PUH, st));
+  RC(pu_permute_split_run(h2h1, pl.hh1p.hi, pl.hh1p.lo, st));
   COPYF(pl.Wp, P[i++], 3 * (PUX + PUH));
   COPYF(pl.bp, P[i++], 3);
   if (pl.global_head) {
@@ -452,6 +468,18 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
     const int F_ld = layer == 0 ? PUH + PUX : 5 * PUH;
     const W2& hh = layer == 0 ? pl.hh0 : pl.hh1;
     float* out = layer == 0 ? pl.H0 : pl.skel;
+    if (persistent_chain()) {
+      // one persistent launch per layer (per chunk of up to 1024 frames = 128 co-resident CTAs)
+      const W2& hp = layer == 0 ? pl.hh0p : pl.hh1p;
+      for (int b0 = 0; b0 < B; b0 += 1024) {
+        const int bc = B - b0 < 1024 ? B - b0 : 1024;
+        RC(pu_chain_run(hp.hi, hp.lo, G + (long long)b0 * J * G_ld, (long long)J * G_ld, G_ld,
+                        F + (long long)b0 * J * F_ld, (long long)J * F_ld, F_ld, out + (long long)b0 * J * PUH,
+                        layer == 0 ? pl.h0b.hi + (long long)b0 * J * PUH : nullptr,
+                        layer == 0 && pl.h0b.lo ? pl.h0b.lo + (long long)b0 * J * PUH : nullptr, pl.hg.hi, pl.hg.lo,
+                        pl.counters, bc, J, pl.nsplit, st));
+      }
+    } else {
     EB_CUDA(cudaMemsetAsync(pl.cst, 0, size_t(B) * PUH * 4, st));
     for (int t = 0; t < J; ++t) {
       const float* gates = G + (long long)t * G_ld;   // t == 0: h = 0, so gates are the x-side term alone
@@ -465,6 +493,7 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
       }
       RC(pu_cell_run(gates, gates_ld, pl.cst, F, F_ld, t, J, PUH, B, out, layer == 0 ? pl.h0b.hi : nullptr,
                      layer == 0 ? pl.h0b.lo : nullptr, pl.hg.hi, pl.hg.lo, st));
+    }
     }
     if (layer == 0) {
       EpiParams e = epi0();
