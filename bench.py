@@ -83,6 +83,8 @@ def time_oracle_cpu(preset, sd, steps, warmup, batch=CPU_SAMPLE_BATCH):
     import torch
     import egotap_oracle as orc
     from egotap_b200.synthetic import synthetic_heatmaps
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core this process may run on
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     x = synthetic_heatmaps(preset, batch, seed=1234, kind="gauss")
     with torch.no_grad():
         for _ in range(warmup):
@@ -206,17 +208,39 @@ def run_ours(args):
     gemm_flops = sum(r["flops"] for r in recs)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     nsplit = 3 if args.precision != "bf16" else 1
+    # DRAM traffic of the same launches from the committed ncu capture (profiles/), when it is for this configuration
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if (tj["batch"], tj["preset"], tj["precision"]) == (B, args.preset, args.precision):
+            traffic = tj["gemm_tc_kernel_bytes_per_step"]
     roofline = dict(bound="tensor", kernel="gemm_tc_kernel (all %d launches of one step)" % len(recs), achieved=achieved,
-                    peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"], traffic=None,
+                    peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"], traffic=traffic,
+                    traffic_note="DRAM bytes of the same GEMM launches of one step (ncu, profiles/r01b_traffic.json)",
                     peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                     mma_passes_per_flop=nsplit, mma_frac=achieved * nsplit / pk["bf16_sustained"],
                     gemm_share_of_step=gemm_ms / (ms / K), note="achieved = algorithmic 2*M*N*K over all GEMM launches of one "
                     "step / their summed CUDA-event durations; bf16x3 issues 3 MMAs per algorithmic FLOP")
+    # HBM-bound kernels: algorithmic bytes per launch / CUDA-event duration vs measured copy peak
+    J = 15 if args.preset == "UnrealEgo" else 17
+    nb = 2 * (2 if nsplit == 3 else 1)                       # bytes per operand element written (bf16 hi [+ lo])
+    rows_ln = B * 576
+    hbm_bytes = {"layernorm1024_kernel": rows_ln * 1024 * (4 + nb),
+                 "ingest_kernel": B * 6 * J * 4096 * (4 + nb)}
+    hbm = {}
+    for name, nbytes in hbm_bytes.items():
+        ts = [r["ms"] for r in all_recs if r["name"] == name]
+        if ts:
+            t = max(ts) if name == "layernorm1024_kernel" else ts[0]   # full-size LN launches (the last one is compacted)
+            hbm[name] = dict(ms=t, bytes=nbytes, achieved_gbs=nbytes / t / 1e6, peak_gbs=pk["hbm_gbs"],
+                             frac=nbytes / t / 1e6 / pk["hbm_gbs"])
     fps = total * K / (ms * 1e-3)
     whole = dict(achieved=fps / world * FLOP_PER_FRAME[args.preset] / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s")
     whole["frac"] = whole["achieved"] / whole["peak"]
     # ---------------- CPU baseline on this box's host cores (bounded sample)
-    cpu = time_oracle_cpu(args.preset, sd, steps=3, warmup=1)
+    cpu = time_oracle_cpu(args.preset, sd, steps=3, warmup=1) if world == 1 else None
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="bf16x3 operands, f32 accumulate" if nsplit == 3 else "bf16 operands, f32 accumulate",
@@ -227,8 +251,10 @@ def run_ours(args):
                 e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pipe.h2d_bytes_per_step,
                          d2h_bytes_per_step=pipe.d2h_bytes_per_step, checked=e2e_ok),
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_whole_step=whole,
-                cpu_baseline=dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
-                                  sample="3 steps x batch %d frames of the same workload, fp32 oracle" % cpu["batch"]),
+                roofline_hbm_kernels=hbm,
+                cpu_baseline=(dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
+                                   sample="3 steps x batch %d frames of the same workload, fp32 oracle" % cpu["batch"])
+                              if cpu else None),
                 parity=parity)
     print(json.dumps(line), flush=True)
     if args.dump:
@@ -242,7 +268,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference"])
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])

@@ -133,6 +133,41 @@ def test_batch_sizes_and_ragged_batches(state_dicts):
     assert orc.parity_report(full, ref)["rel"] <= 5e-4
 
 
+def test_full_size_batch_equals_small_batches(state_dicts):
+    """BASELINE.json's full sizes through a size-independent property: frames are independent, so a batch of 1100
+    (more than one 1024-frame chunk of the persistent chain kernel, several waves of every GEMM) must reproduce,
+    row for row, what the same frames give in batches of 256 / 76 -- which the oracle tests pin at small size."""
+    from egotap_b200 import synthetic_heatmaps
+    preset = "UnrealEgo"
+    net = _module(preset, "bf16x3", state_dicts(preset))
+    base = synthetic_heatmaps(preset, 44, seed=21, kind="gauss").cuda()
+    x = base.repeat(25, 1, 1, 1) * torch.linspace(0.5, 1.5, 1100, device="cuda")[:, None, None, None]
+    big = net.predict_pose(x).clone()
+    parts = torch.cat([net.predict_pose(x[i:i + 256]).clone() for i in range(0, 1024, 256)] + [net.predict_pose(x[1024:]).clone()])
+    assert torch.isfinite(big).all()
+    assert (big - parts).abs().max().item() < 2e-5
+    with torch.no_grad():
+        ref = orc.forward(state_dicts(preset), x[1098:].cpu(), preset)
+    assert orc.parity_report(big[1098:], ref)["rel"] <= 5e-4
+
+
+def test_per_joint_launch_path_agrees_with_persistent_chain(state_dicts):
+    """The persistent propagation-chain kernel vs the per-joint launch sequence it replaced (both CUDA)."""
+    import subprocess, sys, os, json
+    code = ("import sys; sys.path[:0]=[%r,%r]; import torch, weights, egotap_b200; from ref_shim import make_opt;"
+            "net=egotap_b200.EgoTAPAutoEncoder(make_opt('EgoCap'),2); net.load_state_dict(weights.make_state_dict('EgoCap',5));"
+            "net=net.cuda().eval(); x=egotap_b200.synthetic_heatmaps('EgoCap',5,seed=8).cuda();"
+            "print(net.predict_pose(x).flatten().tolist())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"EGOTAP_PU": "steps", "EGOTAP_ATTN": "unfused", "EGOTAP_SKIP_DUMMY": "0"}):
+        r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "oracle"))], capture_output=True,
+                           text=True, env=dict(os.environ, **env), timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.tensor(json.loads(r.stdout.strip().splitlines()[-1])))
+    assert ((outs[0] - outs[1]).abs().max() / outs[1].abs().max()).item() < 2e-4
+
+
 def test_cpu_input_is_an_error_not_a_fallback(state_dicts):
     preset = "EgoCap"
     net = _module(preset, "bf16x3", state_dicts(preset))
