@@ -18,7 +18,8 @@ STORE_ROWMAJOR, STORE_QKV, STORE_JOINT_REGROUP, STORE_HEAD_MERGE = 0, 1, 2, 3
 EXPORTS = [
     "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
     "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
-    "egotap_b200_split_bf16", "egotap_b200_attention", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
+    "egotap_b200_split_bf16", "egotap_b200_attention", "egotap_b200_ingest", "egotap_b200_layernorm",
+    "egotap_b200_pu_permute_split", "egotap_b200_pu_chain", "egotap_b200_head", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
     "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
     "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
 ]
@@ -62,6 +63,12 @@ def lib():
         L.egotap_b200_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
         L.egotap_b200_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.egotap_b200_attention.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]
+        L.egotap_b200_ingest.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.egotap_b200_layernorm.argtypes = [C.c_void_p] * 3 + [C.c_longlong, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 4
+        L.egotap_b200_pu_permute_split.argtypes = [C.c_void_p] * 4
+        L.egotap_b200_pu_chain.argtypes = ([C.c_void_p] * 3 + [C.c_longlong] * 2 + [C.c_void_p] + [C.c_longlong] * 2 +
+                                           [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p])
+        L.egotap_b200_head.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
         L.egotap_b200_param_name.restype = C.c_char_p
         L.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -113,6 +120,60 @@ def attention(qk_hi, qk_lo, vt_hi, vt_lo, frames, precision=PREC_BF16X3):
     check(lib().egotap_b200_attention(_ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
                                       frames, precision, current_stream()), "attention")
     return ctx_hi, ctx_lo
+
+
+def ingest(x, preset):
+    """(B, 6J, 64, 64) fp32 -> (patch_hi, patch_lo, limb_hi, limb_lo) bf16 operand matrices."""
+    import torch
+    require_cuda(x)
+    B, J = x.shape[0], x.shape[1] // 6
+    mk = lambda r, c: torch.empty((r, c), dtype=torch.bfloat16, device=x.device)
+    ph, pl, lh, ll = mk(B * 2 * J * 16, 256), mk(B * 2 * J * 16, 256), mk(B * 2 * J, 8192), mk(B * 2 * J, 8192)
+    check(lib().egotap_b200_ingest(x.data_ptr(), B, PRESET_ID[preset], ph.data_ptr(), pl.data_ptr(), lh.data_ptr(),
+                                   ll.data_ptr(), current_stream()), "ingest")
+    return ph, pl, lh, ll
+
+
+def layernorm(x, w, b, frames, rows_in, rows_out, eps=1e-12):
+    """fp32 (frames*rows_in, 1024) -> (hi, lo, f32) each (frames*rows_out, 1024)."""
+    import torch
+    require_cuda(x, w, b)
+    hi = torch.empty((frames * rows_out, 1024), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    f32 = torch.empty((frames * rows_out, 1024), dtype=torch.float32, device=x.device)
+    check(lib().egotap_b200_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), frames, rows_in, rows_out, eps,
+                                      hi.data_ptr(), lo.data_ptr(), f32.data_ptr(), current_stream()), "layernorm")
+    return hi, lo, f32
+
+
+def pu_chain(w_hh, G, F, frames, J, precision=PREC_BF16X3):
+    """One propagation-unit layer: w_hh (2048, 512) fp32, G (frames*J, 2048) fp32, F (frames*J, 512) fp32
+    -> h (frames*J, 512) fp32."""
+    import torch
+    require_cuda(w_hh, G, F)
+    dev = w_hh.device
+    wh = torch.empty((2048, 512), dtype=torch.bfloat16, device=dev); wl = torch.empty_like(wh)
+    check(lib().egotap_b200_pu_permute_split(w_hh.contiguous().data_ptr(), wh.data_ptr(), wl.data_ptr(), current_stream()),
+          "pu_permute_split")
+    out = torch.empty((frames * J, 512), dtype=torch.float32, device=dev)
+    hg_h = torch.zeros((2 * frames, 512), dtype=torch.bfloat16, device=dev); hg_l = torch.zeros_like(hg_h)
+    cnt = torch.zeros(64, dtype=torch.int32, device=dev)
+    x3 = precision == PREC_BF16X3
+    check(lib().egotap_b200_pu_chain(wh.data_ptr(), wl.data_ptr() if x3 else None, G.data_ptr(), J * G.shape[1], G.shape[1],
+                                     F.data_ptr(), J * F.shape[1], F.shape[1], out.data_ptr(), None, None, hg_h.data_ptr(),
+                                     hg_l.data_ptr() if x3 else None, cnt.data_ptr(), frames, J, precision,
+                                     current_stream()), "pu_chain")
+    return out
+
+
+def head(e, skel, Wp, bp, Wg, bg, frames, J):
+    import torch
+    require_cuda(e, skel, Wp, bp, Wg, bg)
+    nj = J + 1 if Wg is not None else J
+    pose = torch.empty((frames, nj, 3), dtype=torch.float32, device=e.device)
+    check(lib().egotap_b200_head(e.data_ptr(), e.shape[1], skel.data_ptr(), Wp.data_ptr(), bp.data_ptr(), _ptr(Wg), _ptr(bg),
+                                 frames, J, pose.data_ptr(), current_stream()), "head")
+    return pose
 
 
 def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0), a_rows=None,

@@ -574,3 +574,32 @@ extern "C" int egotap_b200_plan_buffer(egotap_plan* p, const char* name, void** 
   *ptr = r;
   return 0;
 }
+
+// ---- op-level entry points (parity tests) ----------------------------------------------------------------
+extern "C" int egotap_b200_ingest(const float* x, int frames, int preset, void* p_hi, void* p_lo, void* l_hi, void* l_lo,
+                                  void* stream) {
+  if (preset != EGOTAP_PRESET_UNREALEGO && preset != EGOTAP_PRESET_EGOCAP) return fail(EGOTAP_E_ARG, "unknown preset");
+  return ingest_run(x, frames, preset == EGOTAP_PRESET_UNREALEGO ? 15 : 17, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
+                    (__nv_bfloat16*)l_hi, (__nv_bfloat16*)l_lo, (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_layernorm(const float* x, const float* w, const float* b, long long frames, int rows_in,
+                                     int rows_out, float eps, void* hi, void* lo, float* out_f32, void* stream) {
+  return layernorm_run(x, w, b, frames, rows_in, rows_out, eps, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, out_f32,
+                       (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_pu_permute_split(const float* w, void* hi, void* lo, void* stream) {
+  if (!w || !hi) return fail(EGOTAP_E_ARG, "pu_permute_split: null pointer");
+  return pu_permute_split_run(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_pu_chain(const void* w_hi, const void* w_lo, const float* G, long long G_rs, long long G_ts,
+                                    const float* F, long long F_rs, long long F_ts, float* out, void* out_hi, void* out_lo,
+                                    void* hg_hi, void* hg_lo, void* counters, int frames, int J, int precision,
+                                    void* stream) {
+  return pu_chain_run((const __nv_bfloat16*)w_hi, (const __nv_bfloat16*)w_lo, G, G_rs, G_ts, F, F_rs, F_ts, out,
+                      (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, (__nv_bfloat16*)hg_hi, (__nv_bfloat16*)hg_lo,
+                      (unsigned int*)counters, frames, J, precision == EGOTAP_PREC_BF16 ? 1 : 3, (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_head(const float* e, int e_ld, const float* skel, const float* Wp, const float* bp,
+                                const float* Wg, const float* bg, long long frames, int J, float* pose, void* stream) {
+  return head_run(e, e_ld, skel, Wp, bp, Wg, bg, frames, J, PUX, PUH, pose, (cudaStream_t)stream);
+}

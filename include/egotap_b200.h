@@ -99,6 +99,31 @@ const char* egotap_b200_gemm_variant_name(int variant);
 int egotap_b200_attention(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, void* ctx_hi,
                           void* ctx_lo, int frames, int precision, void* stream);
 
+/* Op level: the bandwidth-bound kernels and the persistent propagation chain, for op-level parity tests.
+ *
+ * ingest: (frames, 6J, 64, 64) fp32 heatmaps -> patch-embedding operand (frames*2J*16, 256) and limb operand
+ *   (frames*2J, 8192) as bf16 hi/lo (reference model/net_architecture.py:688-694, :375-383, modeling_vit.py:195).
+ * layernorm: LayerNorm over 1024 features of rows [frame*rows_in + tok], tok < rows_out, written compacted to
+ *   row frame*rows_out + tok as bf16 hi/lo and/or fp32 (reference model/modeling_vit.py:367,378,609).
+ * pu_permute_split: W_hh (2048 x 512 fp32, gate order f,i,g,o) -> gate-permuted bf16 hi/lo for pu_chain.
+ * pu_chain: one propagation-unit layer over all J joints (reference model/custom_cells.py:94-120,149-197):
+ *   gates[b,t] = G[b*G_rs + t*G_ts + :2048] + (sigmoid(F[b*F_rs + t*F_ts + :512]) * h[b,t-1]) . W_hh^T,
+ *   h -> out[(b*J + t)*512 + :] (fp32, optional bf16 hi/lo); hg: scratch 2*frames*512 bf16 (hi, lo);
+ *   counters: >= ceil(frames/256) 32-bit words; frames <= 1024 per call.
+ * head: per-joint Linear(768->3) on [e[b*J+j, :256] | skel[b*J+j, :512]], optional global Linear(J*512->6) whose
+ *   first 3 outputs are added to every joint and last 3 appended as the LAST joint
+ *   (reference model/net_architecture.py:732-751). */
+int egotap_b200_ingest(const float* heatmaps, int frames, int preset, void* patch_hi, void* patch_lo, void* limb_hi,
+                       void* limb_lo, void* stream);
+int egotap_b200_layernorm(const float* x, const float* weight, const float* bias, long long frames, int rows_in,
+                          int rows_out, float eps, void* out_hi, void* out_lo, float* out_f32, void* stream);
+int egotap_b200_pu_permute_split(const float* w_hh, void* w_hi, void* w_lo, void* stream);
+int egotap_b200_pu_chain(const void* w_hi, const void* w_lo, const float* G, long long G_rs, long long G_ts,
+                         const float* F, long long F_rs, long long F_ts, float* out, void* out_hi, void* out_lo,
+                         void* hg_hi, void* hg_lo, void* counters, int frames, int J, int precision, void* stream);
+int egotap_b200_head(const float* e, int e_ld, const float* skel, const float* Wp, const float* bp, const float* Wg,
+                     const float* bg, long long frames, int J, float* pose, void* stream);
+
 /* Per-launch CUDA-event timing of every kernel launched between begin and end (bench.py's live roofline
  * measurement; events are recorded on the launching stream).  end() synchronises the device.  GEMM records
  * carry their shape; other kernels report M = N = K = 0. */
