@@ -71,7 +71,39 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * phi;
 }
 
-__device__ __forceinline__ void epi_apply(const EpiParams& p, int g, int m, int n0, int N, uint32_t (&r)[32]) {
+// Per-thread row mapping of the epilogue (computed once per tile): output row, residual row, column shift.
+struct EpiRow {
+  long long orow, rrow;
+  int col_shift;
+};
+__device__ __forceinline__ EpiRow epi_row(const EpiParams& p, int g, int m, int N) {
+  EpiRow r;
+  r.col_shift = 0;
+  if (p.store == STORE_JOINT_REGROUP) {
+    const int frame = m / (2 * p.J), rem = m % (2 * p.J);
+    const int view = rem / p.J, j = rem % p.J;
+    r.orow = (long long)frame * p.J + j;
+    r.col_shift = view * N;
+  } else if (p.store == STORE_HEAD_MERGE) {
+    r.orow = (long long)(g / p.heads) * p.tokens + m;
+    r.col_shift = (g % p.heads) * N;
+  } else {
+    r.orow = (p.rows_in > 0) ? (long long)(m / p.rows_in) * p.rows_out + (m % p.rows_in) : (long long)m;
+    r.orow += (long long)g * p.group_rows;
+  }
+  r.rrow = p.resid_mod > 0 ? (long long)(m % p.resid_mod) : r.orow;
+  return r;
+}
+// Residual / additive-table chunk of 32 columns; issued BEFORE the accumulator chunk is waited for so the
+// (row-strided, DRAM-latency) loads overlap the TMEM read and the previous chunk's math.
+__device__ __forceinline__ void epi_load_resid(const EpiParams& p, const EpiRow& row, int n0, float4 (&t)[8]) {
+  const float4* r4 = reinterpret_cast<const float4*>(p.resid + row.rrow * p.resid_ld + n0 + p.col_off + row.col_shift);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = r4[j];
+}
+
+__device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
+                                          const float4 (&t)[8]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -98,27 +130,12 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, int g, int m, int 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
   }
-  long long orow;
-  int col = n0 + p.col_off;
-  if (p.store == STORE_JOINT_REGROUP) {
-    int frame = m / (2 * p.J), rem = m % (2 * p.J);
-    int view = rem / p.J, j = rem % p.J;
-    orow = (long long)frame * p.J + j;
-    col += view * N;
-  } else if (p.store == STORE_HEAD_MERGE) {
-    orow = (long long)(g / p.heads) * p.tokens + m;
-    col += (g % p.heads) * N;
-  } else {
-    orow = (p.rows_in > 0) ? (long long)(m / p.rows_in) * p.rows_out + (m % p.rows_in) : (long long)m;
-    orow += (long long)g * p.group_rows;
-  }
+  const long long orow = row.orow;
+  const int col = n0 + p.col_off + row.col_shift;
   if (p.resid) {
-    long long rrow = p.resid_mod > 0 ? (long long)(m % p.resid_mod) : orow;
-    const float4* r4 = reinterpret_cast<const float4*>(p.resid + rrow * p.resid_ld + col);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 t = r4[j];
-      v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+      v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
     }
   }
   if (p.store == STORE_QKV && n0 >= p.qk_cols) {
@@ -301,14 +318,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       tc_fence_after();
       const int m = m_blk * C::BM * CG + cta_rank * C::BM + q * 32 + lane;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+      const bool row_ok = m < s.M;
+      const bool use_resid = ep.resid != nullptr && row_ok;
+      const EpiRow row = epi_row(ep, g, row_ok ? m : 0, s.N);
+      float4 t_cur[8], t_nxt[8];
+      const int n_first = n_blk * BN + col_base;
+      if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur);
 #pragma unroll 1
       for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
-        const int n0 = n_blk * BN + col_base + c * 32;
+        const int n0 = n_first + c * 32;
         if (n0 >= s.N) break;
         uint32_t r[32];
         tmem_ld32(t_addr + col_base + c * 32, r);
+        const bool more = (c + 1 < C::COLS_PER_EPI_GROUP / 32) && (n0 + 32 < s.N);
+        if (use_resid && more) epi_load_resid(ep, row, n0 + 32, t_nxt);   // prefetch the next chunk's residual
         tmem_ld_wait();
-        if (m < s.M) epi_apply(ep, g, m, n0, s.N, r);
+        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur);
+        if (use_resid && more) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];
+        }
       }
       tc_fence_before();
       __syncwarp();
