@@ -115,6 +115,38 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_torch_eager(args):
+    """Context arm (not part of the driver contract): the SAME algorithm through stock PyTorch eager kernels
+    (cuBLAS / ATen) on the GPU -- the 'kernel to beat on the same box', since the reference ships no CUDA of its
+    own.  Uses the oracle restatement, fp32 (TF32 off) and bf16 autocast."""
+    import torch
+    import egotap_oracle as orc
+    import weights
+    from egotap_b200.synthetic import synthetic_heatmaps
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: v.to(dev) for k, v in weights.make_state_dict(args.preset, seed=0, randomize=False).items()}
+    x = synthetic_heatmaps(args.preset, args.batch, seed=1234, kind="gauss").to(dev)
+    out = {}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        with torch.no_grad(), ctx:
+            for _ in range(max(1, args.warmup)):
+                orc.forward(sd, x, args.preset)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                orc.forward(sd, x, args.preset)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = dict(value=args.batch / ms * 1e3, unit="frames/s", ms_per_step=ms)
+    print(json.dumps(dict(impl="torch_eager", metric=METRIC, n_gpus=1, steps=args.steps, warmup=args.warmup,
+                          config=dict(workload=workload_name(args), preset=args.preset, batch_per_gpu=args.batch),
+                          value=out["fp32"]["value"], unit="frames/s", dtype="f32 (TF32 off)", arms=out)), flush=True)
+
+
 def workload_name(args):
     return "EgoTAP lifting net (3-layer ViT heatmap encoder + limb FC encoder + 2-layer propagation chain + head), " \
            "%s preset, random-init weights, synthetic stereo joint+limb heatmaps 64x64, batch %d per GPU" % (args.preset, args.batch)
@@ -270,7 +302,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference"])
+    ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference", "torch_eager"])
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
@@ -280,6 +312,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_eager":
+        run_torch_eager(args)
     else:
         if args.gpus > 1 and "RANK" not in os.environ:
             raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "

@@ -19,7 +19,7 @@ EXPORTS = [
     "egotap_b200_abi_version", "egotap_b200_last_error", "egotap_b200_launch_count",
     "egotap_b200_gemm", "egotap_b200_gemm_num_variants", "egotap_b200_gemm_variant_name",
     "egotap_b200_split_bf16", "egotap_b200_attention", "egotap_b200_ingest", "egotap_b200_layernorm",
-    "egotap_b200_pu_permute_split", "egotap_b200_pu_chain", "egotap_b200_head", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
+    "egotap_b200_pu_permute_split", "egotap_b200_pu_chain", "egotap_b200_head", "egotap_b200_pose_metrics", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
     "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
     "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
 ]
@@ -69,6 +69,8 @@ def lib():
         L.egotap_b200_pu_chain.argtypes = ([C.c_void_p] * 3 + [C.c_longlong] * 2 + [C.c_void_p] + [C.c_longlong] * 2 +
                                            [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p])
         L.egotap_b200_head.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+        L.egotap_b200_pose_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
         L.egotap_b200_param_name.restype = C.c_char_p
         L.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]

@@ -124,6 +124,13 @@ int egotap_b200_pu_chain(const void* w_hi, const void* w_lo, const float* G, lon
 int egotap_b200_head(const float* e, int e_ld, const float* skel, const float* Wp, const float* bp, const float* Wg,
                      const float* bg, long long frames, int J, float* pose, void* stream);
 
+/* Evaluation metrics: per-frame MPJPE and Procrustes-aligned MPJPE of pred vs gt poses
+ * (frames, joints, 3), multiplied by unit_scale (10 = cm -> mm).  Replaces batch_compute_similarity_transform_torch
+ * + the per-frame metric loop (reference utils/util.py:328-379, utils/evaluate.py:54-73,
+ * model/egotap_autoencoder_model.py:336-348). */
+int egotap_b200_pose_metrics(const float* pred, const float* gt, long long frames, int joints, float unit_scale,
+                             float* mpjpe, float* pa_mpjpe, void* stream);
+
 /* Per-launch CUDA-event timing of every kernel launched between begin and end (bench.py's live roofline
  * measurement; events are recorded on the launching stream).  end() synchronises the device.  GEMM records
  * carry their shape; other kernels report M = N = K = 0. */

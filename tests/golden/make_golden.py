@@ -47,5 +47,24 @@ def main():
             print("wrote", path, pose.shape)
 
 
+def metrics_golden():
+    """Evaluation-metric golden: the reference's own Procrustes + MPJPE on seeded poses."""
+    ref_shim.import_reference()
+    from utils.loss import LossFuncMPJPE
+    from utils.util import batch_compute_similarity_transform_torch
+    g = torch.Generator().manual_seed(3)
+    gt = torch.randn(6, 16, 3, generator=g) * 20
+    pred = gt + torch.randn(6, 16, 3, generator=g) * 3
+    pred[1] = gt[1] @ torch.tensor([[0., 1, 0], [1, 0, 0], [0, 0, 1]])      # a mirrored pose (det < 0 branch)
+    S = batch_compute_similarity_transform_torch(pred, gt)
+    lf = LossFuncMPJPE()
+    m = torch.stack([lf(pred[i], gt[i]) * 10 for i in range(6)])
+    pa = torch.stack([lf(S[i], gt[i]) * 10 for i in range(6)])
+    np.savez_compressed(os.path.join(HERE, "ref_metrics.npz"), pred=pred.numpy(), gt=gt.numpy(), mpjpe_mm=m.numpy(),
+                        pa_mpjpe_mm=pa.numpy())
+    print("wrote ref_metrics.npz")
+
+
 if __name__ == "__main__":
     main()
+    metrics_golden()
