@@ -148,6 +148,9 @@ def run_torch_eager(args):
 
 
 def workload_name(args):
+    if getattr(args, "workload", "lifting") == "e2e_rgb":
+        return "stereo RGB 256x256 -> 2 x ResNet-18 U-Net heatmap producers (torch/cuDNN, bf16 autocast) -> EgoTAP " \
+               "lifting net (sm_100a kernels), %s preset, random-init weights, batch %d per GPU" % (args.preset, args.batch)
     return "EgoTAP lifting net (3-layer ViT heatmap encoder + limb FC encoder + 2-layer propagation chain + head), " \
            "%s preset, random-init weights, synthetic stereo joint+limb heatmaps 64x64, batch %d per GPU" % (args.preset, args.batch)
 
@@ -181,9 +184,21 @@ def run_ours(args):
     x_host = egotap_b200.synthetic_heatmaps(args.preset, B, seed=1234 + rank, kind="gauss").pin_memory()
     x = x_host.to(dev)
     total = B * world
+    est = None
+    if args.workload == "e2e_rgb":
+        # BASELINE config 4: torch/cuDNN ResNet-18 U-Net heatmap producers (random init) feeding the lifting kernels
+        from egotap_b200.heatmap_net import HeatMapUNet, StereoPoseEstimator
+        pos_opt, rot_opt = make_opt(args.preset), make_opt(args.preset)
+        pos_opt.num_rot_heatmap = 0
+        rot_opt.num_heatmap = 0
+        est = StereoPoseEstimator(HeatMapUNet(pos_opt).to(dev).to(memory_format=torch.channels_last),
+                                  HeatMapUNet(rot_opt).to(dev).to(memory_format=torch.channels_last), net).eval()
+        g = torch.Generator().manual_seed(77 + rank)
+        rgb_host = [torch.rand(B, 3, 256, 256, generator=g).pin_memory() for _ in range(2)]
+        rgb = [t.to(dev) for t in rgb_host]
 
     def step():
-        pose = net.predict_pose(x)
+        pose = est(rgb[0], rgb[1]) if est is not None else net.predict_pose(x)
         return gather_poses(pose, total) if world > 1 else pose
 
     for _ in range(W):
@@ -193,7 +208,8 @@ def run_ours(args):
     parity = None
     if rank == 0:
         with torch.no_grad():
-            ref = orc.forward(sd, x_host[:2], args.preset)
+            ref_in = est.pred_heatmap_cat[:2].cpu() if est is not None else x_host[:2]
+            ref = orc.forward(sd, ref_in, args.preset)
         parity = orc.parity_report(pose[:2], ref)
     # ---------------- timed region: inputs resident in HBM
     launches0 = capi.lib().egotap_b200_launch_count()
@@ -210,16 +226,31 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = capi.lib().egotap_b200_launch_count() - launches0
     # ---------------- end to end: pinned host buffers in, pinned host poses out, copies inside the timed region
-    pipe = HostPipeline(net, B)
-    host_in = [x_host, x_host.clone().pin_memory()]
     host_out = [torch.empty((B, net.num_joints, 3)).pin_memory() for _ in range(K)]
-    pipe.run([host_in[i % 2] for i in range(min(W, 2))], host_out)
+    if est is None:
+        pipe = HostPipeline(net, B)
+        host_in = [x_host, x_host.clone().pin_memory()]
+        pipe.run([host_in[i % 2] for i in range(min(W, 2))], host_out)
+        h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+
+        def run_e2e():
+            pipe.run([host_in[i % 2] for i in range(K)], host_out)
+    else:
+        h2d, d2h = 2 * rgb_host[0].numel() * 4, B * net.num_joints * 3 * 4
+
+        def run_e2e():
+            for i in range(K):
+                l = rgb_host[0].to(dev, non_blocking=True)
+                r = rgb_host[1].to(dev, non_blocking=True)
+                host_out[i].copy_(est(l, r), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        run_e2e()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    pipe.run([host_in[i % 2] for i in range(K)], host_out)
+    run_e2e()
     t1.record()
     torch.cuda.synchronize()
     ms_e2e = t0.elapsed_time(t1)
@@ -234,7 +265,7 @@ def run_ours(args):
     e2e_ok = bool(torch.isfinite(host_out[-1]).all()) and (host_out[-1][:2].to(dev) - pose[:2]).abs().max().item() < 1e-5
     # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), per-launch CUDA events, one extra step
     pk = peaks()
-    all_recs = capi.profile_kernels(lambda: net.predict_pose(x))
+    all_recs = capi.profile_kernels(lambda: step())
     recs = [r for r in all_recs if "flops" in r]
     gemm_ms = sum(r["ms"] for r in recs)
     gemm_flops = sum(r["flops"] for r in recs)
@@ -269,7 +300,8 @@ def run_ours(args):
             hbm[name] = dict(ms=t, bytes=nbytes, achieved_gbs=nbytes / t / 1e6, peak_gbs=pk["hbm_gbs"],
                              frac=nbytes / t / 1e6 / pk["hbm_gbs"])
     fps = total * K / (ms * 1e-3)
-    whole = dict(achieved=fps / world * FLOP_PER_FRAME[args.preset] / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s")
+    flop_frame = FLOP_PER_FRAME[args.preset] + (107.41e9 if est is not None else 0.0)   # + producers
+    whole = dict(achieved=fps / world * flop_frame / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s")
     whole["frac"] = whole["achieved"] / whole["peak"]
     # ---------------- CPU baseline on this box's host cores (bounded sample)
     cpu = time_oracle_cpu(args.preset, sd, steps=3, warmup=1) if world == 1 else None
@@ -280,8 +312,8 @@ def run_ours(args):
                 config=dict(workload=workload_name(args), preset=args.preset, batch_per_gpu=B, global_batch=total,
                             precision=args.precision, parallelism="dp%d (frames sharded, final pose gather)" % world,
                             l2="inputs %.0f MB + activations >> 126 MB L2 per step, no flush needed" % (x.numel() * 4 / 1e6)),
-                e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=pipe.h2d_bytes_per_step,
-                         d2h_bytes_per_step=pipe.d2h_bytes_per_step, checked=e2e_ok),
+                e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h, checked=e2e_ok),
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_whole_step=whole,
                 roofline_hbm_kernels=hbm,
                 cpu_baseline=(dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
@@ -306,6 +338,8 @@ def main():
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--workload", default="lifting", choices=["lifting", "e2e_rgb"],
+                    help="lifting = BASELINE configs 1-3 (default); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting)")
     ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

@@ -1,0 +1,137 @@
+"""Stereo heatmap PRODUCER for BASELINE config 4 -- torch / cuDNN, by design.
+
+The reference's ResNet-U-Net heatmap estimator (``HeatMap_UnrealEgo_Shared``, reference
+``model/net_architecture.py:25-173``) is OUT OF SCOPE for hand-written kernels: it stays a
+PyTorch module.  This file is a state_dict-compatible mirror so that config 4 can be assembled where the reference
+tree is absent (the GPU box): a shared torchvision ResNet backbone applied per view, per-level channel
+concatenation of the two views, 1x1 lateral convs, three bilinear-upsample + 3x3 conv stages and a final 1x1 conv to
+``2 * n_heatmaps`` channels at 64x64.  ``tests/test_heatmap_net.py`` checks it against the reference module live.
+
+What IS built natively here is the hand-off (``StereoPoseEstimator``): both producers write straight into the
+channel slices of ONE persistent ``(B, 6J, 64, 64)`` fp32 buffer in the lifting net's layout
+``[joint L | joint R | cos L | sin L | cos R | sin R]`` (reference ``model/egotap_autoencoder_model.py:177-216``
+builds it with three ``torch.cat`` copies per batch), and the lifting path consumes that buffer in place.
+"""
+import torch
+import torch.nn as nn
+import torchvision
+
+
+def _convrelu(cin, cout, k, pad):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, padding=pad), nn.ReLU(inplace=True))
+
+
+class _Encoder(nn.Module):
+    """torchvision ResNet split into the five feature levels (keys: backbone.* and the layer0..4 aliases)."""
+
+    def __init__(self, model_name):
+        super().__init__()
+        self.backbone = getattr(torchvision.models, model_name)(weights=None)
+        ch = list(self.backbone.children())
+        self.layer0 = nn.Sequential(*ch[:3])      # /2
+        self.layer1 = nn.Sequential(*ch[3:5])     # /4
+        self.layer2, self.layer3, self.layer4 = ch[5], ch[6], ch[7]   # /8, /16, /32
+
+    def forward(self, x):
+        f0 = self.layer0(x)
+        f1 = self.layer1(f0)
+        f2 = self.layer2(f1)
+        f3 = self.layer3(f2)
+        return [x, f0, f1, f2, f3, self.layer4(f3)]
+
+
+class _SharedBackbone(nn.Module):
+    def __init__(self, model_name):
+        super().__init__()
+        self.backbone = _Encoder(model_name)
+
+    def forward(self, *views):
+        return tuple(self.backbone(v) for v in views)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, n_out, model_name, views):
+        super().__init__()
+        fs = (4 if model_name in ("resnet50", "resnet101") else 1) * views
+        self.layer1_1x1 = _convrelu(64 * fs, 64 * fs, 1, 0)
+        self.layer2_1x1 = _convrelu(128 * fs, 128 * fs, 1, 0)
+        self.layer3_1x1 = _convrelu(256 * fs, 258 * fs, 1, 0)      # 258, not 256: reference quirk (:123)
+        self.layer4_1x1 = _convrelu(512 * fs, 512 * fs, 1, 0)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv_up3 = _convrelu((258 + 512) * fs, 512 * fs, 3, 1)
+        self.conv_up2 = _convrelu((128 + 512) * fs, 256 * fs, 3, 1)
+        self.conv_up1 = _convrelu((64 + 256) * fs, 256 * fs, 3, 1)
+        self.conv_heatmap = nn.Conv2d(256 * fs, n_out * views, 1)
+
+    def forward(self, *per_view):
+        lv = [torch.cat([v[i] for v in per_view], dim=1) for i in range(6)]
+        x = self.upsample(self.layer4_1x1(lv[5]))
+        x = self.conv_up3(torch.cat([x, self.layer3_1x1(lv[4])], dim=1))
+        x = self.conv_up2(torch.cat([self.upsample(x), self.layer2_1x1(lv[3])], dim=1))
+        x = self.conv_up1(torch.cat([self.upsample(x), self.layer1_1x1(lv[2])], dim=1))
+        return self.conv_heatmap(x)
+
+
+class HeatMapUNet(nn.Module):
+    """Mirror of reference ``HeatMap_UnrealEgo_Shared(opt, model_name, input_channel_scale)``."""
+
+    def __init__(self, opt, model_name="resnet18", input_channel_scale=2):
+        super().__init__()
+        limb_dim = {"none": 0, "sin": 2, "limb": 1}[opt.heatmap_type]
+        n_out = opt.num_heatmap + opt.num_rot_heatmap * limb_dim
+        self.backbone = _SharedBackbone(model_name)
+        self.after_backbone = _Decoder(n_out, model_name, input_channel_scale)
+
+    def forward(self, *views):
+        return self.after_backbone(*self.backbone(*views))
+
+
+def define_HeatMap(opt, model):
+    """reference model/network.py:11-22 (without the ImageNet download: there is no network here)."""
+    views = 2 if opt.stereo else 1
+    if model not in ("egotap_autoencoder", "heatmap_shared"):
+        raise Exception("HeatMap is not implemented for {}".format(model))
+    net = HeatMapUNet(opt, getattr(opt, "model_name", "resnet18"), input_channel_scale=views)
+    if len(getattr(opt, "gpu_ids", [])) > 0:
+        net.cuda()
+    return net
+
+
+class StereoPoseEstimator(nn.Module):
+    """RGB stereo pair -> 3D pose: joint-heatmap net + limb-heatmap net (torch) -> lifting net (sm_100a kernels).
+
+    Mirrors the evaluate-time data flow of reference ``EgoTAPAutoEncoderModel.forward_heatmap`` + ``forward``
+    (``model/egotap_autoencoder_model.py:177-237``) with the heatmaps written once, in place, into the lifting
+    net's input buffer."""
+
+    def __init__(self, net_HeatMap, net_RotHeatMap, net_AutoEncoder, producer_dtype=torch.bfloat16):
+        super().__init__()
+        self.net_HeatMap, self.net_RotHeatMap, self.net_AutoEncoder = net_HeatMap, net_RotHeatMap, net_AutoEncoder
+        self.producer_dtype = producer_dtype
+        self._buf = None
+
+    def heatmap_buffer(self, batch, device):
+        """The persistent (B, 6J, 64, 64) fp32 lifting input and its two producer slots (views, no copies)."""
+        C = self.net_AutoEncoder.channels_heatmap
+        if self._buf is None or self._buf.shape[0] < batch or self._buf.device != device:
+            self._buf = torch.empty((batch, C, 64, 64), dtype=torch.float32, device=device)
+        buf = self._buf[:batch]
+        n_pos = 2 * self.net_AutoEncoder.num_pos_heatmap
+        return buf, buf[:, :n_pos], buf[:, n_pos:]
+
+    @torch.no_grad()
+    def forward(self, rgb_left, rgb_right):
+        B, dev = rgb_left.shape[0], rgb_left.device
+        buf, pos_slot, rot_slot = self.heatmap_buffer(B, dev)
+        if self.producer_dtype is not None and dev.type == "cuda":
+            l = rgb_left.contiguous(memory_format=torch.channels_last)
+            r = rgb_right.contiguous(memory_format=torch.channels_last)
+            with torch.autocast("cuda", dtype=self.producer_dtype):
+                pos = self.net_HeatMap(l, r)
+                rot = self.net_RotHeatMap(l, r)
+        else:
+            pos, rot = self.net_HeatMap(rgb_left, rgb_right), self.net_RotHeatMap(rgb_left, rgb_right)
+        pos_slot.copy_(pos)       # one fused cast+copy per producer, straight into the consumer's layout
+        rot_slot.copy_(rot)
+        self.pred_heatmap_cat = buf
+        return self.net_AutoEncoder.predict_pose(buf)
