@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 lib = os.path.join(ROOT, "tools", "libtrace.so")
 if not os.path.isfile(lib) or "--build" in sys.argv:
     os.makedirs(os.path.dirname(lib), exist_ok=True)
-    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "plan.cu")]
+    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "metrics.cu", "plan.cu")]
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
                            "-DEB_ATTN_TRACE", "-o", lib] + src)
 if "--build" in sys.argv:
