@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                  const __grid_constant__ CUtensorMap tmKh, const __grid_constant__ CUtensorMap tmKl,
                  const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
-                 __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items) {
+                 __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items, int qtiles) {
   using C = AttnCfg<NSPLIT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
@@ -151,7 +151,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       const long long tr_start_ = clock64();
 #endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int qt = item % AT_QTILES, bh = item / AT_QTILES;
+        const int qt = item % qtiles, bh = item / qtiles;
         const int h = bh % AT_HEADS, b = bh / AT_HEADS;
         TR_WAIT(1, mbar_wait(q_empty, (it & 1) ^ 1));
         mbar_expect_tx(q_full, C::Q_BYTES);
@@ -350,7 +350,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
     const long long tr_start_ = clock64();
 #endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int qt = item % AT_QTILES, bh = item / AT_QTILES;
+      const int qt = item % qtiles, bh = item / qtiles;
       const int h = bh % AT_HEADS, b = bh / AT_HEADS;
       const int ob = it & 1;
       TR_WAIT(1, mbar_wait(&o_full[ob], (it >> 1) & 1));
@@ -397,7 +397,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
 }
 
 template <int NSPLIT>
-static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B,
+static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int qtiles,
                             cudaStream_t stream) {
   using C = AttnCfg<NSPLIT>;
   auto kern = attention_kernel<NSPLIT>;
@@ -406,18 +406,21 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  const int items = B * AT_HEADS * AT_QTILES;
+  const int items = B * AT_HEADS * qtiles;
   const int grid = items < num_sms() ? items : num_sms();
   ProfScope prof("attention_kernel", stream);
-  kern<<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ctx_hi, ctx_lo, items);
+  kern<<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ctx_hi, ctx_lo, items, qtiles);
   EB_CHECK_LAUNCH("attention_kernel");
   return 0;
 }
 
 // qk: (B*576, 2048) = [Q | K] per token, head h at columns h*128; vt: (B*8*128, 576) = V^T per (frame, head)
+// query_rows: only the first query_rows tokens of every frame get a context row (all 576 are keys / values)
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
-                  cudaStream_t stream) {
+                  int query_rows, cudaStream_t stream) {
+  EB_REQUIRE(query_rows > 0 && query_rows <= AT_TOK, "attention: query_rows must be in (0, 576]");
+  const int qtiles = (query_rows + AT_QT - 1) / AT_QT;
   EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");
   EB_REQUIRE(nsplit == 1 || (qk_lo && vt_lo && ctx_lo), "attention: bf16x3 mode needs the lo parts");
   CUtensorMap tm[6];
@@ -434,8 +437,8 @@ int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const 
       return rc;
   }
   if (nsplit == 1) { tm[1] = tm[0]; tm[3] = tm[2]; tm[5] = tm[4]; }
-  return nsplit == 3 ? launch_attention<3>(tm, ctx_hi, ctx_lo, B, stream)
-                     : launch_attention<1>(tm, ctx_hi, ctx_lo, B, stream);
+  return nsplit == 3 ? launch_attention<3>(tm, ctx_hi, ctx_lo, B, qtiles, stream)
+                     : launch_attention<1>(tm, ctx_hi, ctx_lo, B, qtiles, stream);
 }
 
 }  // namespace eb
@@ -452,5 +455,5 @@ extern "C" int egotap_b200_attention(const void* qk_hi, const void* qk_lo, const
                                      void* ctx_hi, void* ctx_lo, int frames, int precision, void* stream) {
   return eb::attention_run((const __nv_bfloat16*)qk_hi, (const __nv_bfloat16*)qk_lo, (const __nv_bfloat16*)vt_hi,
                            (const __nv_bfloat16*)vt_lo, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo, frames,
-                           precision == EGOTAP_PREC_BF16 ? 1 : 3, (cudaStream_t)stream);
+                           precision == EGOTAP_PREC_BF16 ? 1 : 3, eb::AT_TOK, (cudaStream_t)stream);
 }

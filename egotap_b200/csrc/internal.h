@@ -23,7 +23,7 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
 // attention.cu
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
-                  cudaStream_t stream);
+                  int query_rows, cudaStream_t stream);
 
 // pu_chain.cu
 int pu_permute_split_run(const float* W, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);

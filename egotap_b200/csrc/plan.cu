@@ -384,7 +384,9 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
     }
     if (fused_attention()) {
       // K6: fused softmax attention, scores stay in TMEM / shared memory
-      RC(attention_run(pl.qk.hi, pl.qk.lo, pl.vt.hi, pl.vt.lo, pl.ctx.hi, pl.ctx.lo, B, pl.nsplit, st));
+      // in the last layer only the live tokens need a context row (their dummy-row successors are never read)
+      const int qrows = (l == NLAYERS - 1 && skip_dummy_rows()) ? live : TOK;
+      RC(attention_run(pl.qk.hi, pl.qk.lo, pl.vt.hi, pl.vt.lo, pl.ctx.hi, pl.ctx.lo, B, pl.nsplit, qrows, st));
     } else {
       {  // K6a: scores S[b,h] = Q K^T / sqrt(128)
         EpiParams e = epi0();

@@ -247,6 +247,8 @@ class EgoTAPAutoEncoder(nn.Module):
             x = x.float()
         x = x.contiguous()
         B = x.size(0)
+        if B == 0:     # an empty batch is legal in the reference (every torch op accepts it): nothing to launch
+            return torch.empty((0, self.num_joints, 3), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             self._ensure_plan(B, x.device)
             self._ensure_packed()

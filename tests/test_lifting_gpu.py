@@ -168,6 +168,37 @@ def test_per_joint_launch_path_agrees_with_persistent_chain(state_dicts):
     assert ((outs[0] - outs[1]).abs().max() / outs[1].abs().max()).item() < 2e-4
 
 
+def test_empty_ragged_and_odd_inputs(state_dicts):
+    """Edge cases the reference accepts: empty batch, fp16 / fp64 heatmaps, a non-contiguous view, a second CUDA
+    stream; all-zero heatmaps (an undetected person) must give finite poses."""
+    from egotap_b200 import synthetic_heatmaps
+    preset = "UnrealEgo"
+    sd = state_dicts(preset)
+    net = _module(preset, "bf16x3", sd)
+    x = synthetic_heatmaps(preset, 3, seed=31, kind="gauss").cuda()
+    base = net.predict_pose(x).clone()
+    out = net(x[:0])
+    assert out[0].shape == (0, 16, 3) and out[3].shape == (0, 90, 64, 64)
+    assert (net.predict_pose(x.double()) - base).abs().max() < 1e-6
+    half = net.predict_pose(x.half())
+    with torch.no_grad():
+        ref_half = orc.forward(sd, x.half().float().cpu(), preset)
+    assert orc.parity_report(half, ref_half)["rel"] <= 5e-4
+    wide = torch.zeros(3, 90, 64, 128, device="cuda")
+    wide[..., ::2] = x
+    assert (net.predict_pose(wide[..., ::2]) - base).abs().max() < 1e-6
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        on_side = net.predict_pose(x).clone()
+    side.synchronize()
+    assert (on_side - base).abs().max() < 1e-6
+    zeros = net.predict_pose(torch.zeros_like(x))
+    with torch.no_grad():
+        ref0 = orc.forward(sd, torch.zeros(1, 90, 64, 64), preset)
+    assert torch.isfinite(zeros).all() and orc.parity_report(zeros[:1], ref0)["rel"] <= 5e-4
+
+
 def test_cpu_input_is_an_error_not_a_fallback(state_dicts):
     preset = "EgoCap"
     net = _module(preset, "bf16x3", state_dicts(preset))
