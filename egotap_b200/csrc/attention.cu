@@ -401,10 +401,12 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
                             cudaStream_t stream) {
   using C = AttnCfg<NSPLIT>;
   auto kern = attention_kernel<NSPLIT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
+  static bool attr_done[64] = {false};
+  const int dev_ = current_device();
+  if (!attr_done[dev_]) {
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev_] = true;
   }
   const int items = B * AT_HEADS * qtiles;
   const int grid = items < num_sms() ? items : num_sms();

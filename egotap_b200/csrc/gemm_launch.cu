@@ -11,10 +11,12 @@ template <int CG, int BN, int NS, int ST>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
   using C = GemmCfg<CG, BN, NS, ST>;
   auto kern = gemm_tc_kernel<CG, BN, NS, ST>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
+  static bool attr_done[64] = {false};
+  const int dev_ = current_device();
+  if (!attr_done[dev_]) {
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev_] = true;
   }
   const int nM = (s.M + C::BM * CG - 1) / (C::BM * CG);
   const int nN = (s.N + BN - 1) / BN;

@@ -116,14 +116,17 @@ inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, lon
   return 0;
 }
 
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
+
 inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[64] = {0};
+  const int dev = current_device();
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 }  // namespace eb

@@ -282,10 +282,12 @@ template <int NSPLIT>
 static int launch_pu(const CUtensorMap* tm, const PuParams& p, int groups, cudaStream_t stream) {
   using C = PuCfg<NSPLIT>;
   auto kern = pu_chain_kernel<NSPLIT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
+  static bool attr_done[64] = {false};
+  const int dev_ = current_device();
+  if (!attr_done[dev_]) {
     EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[dev_] = true;
   }
   ProfScope prof("pu_chain_kernel", stream);
   kern<<<groups * PC_SLICES, 192, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
