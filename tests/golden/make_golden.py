@@ -65,6 +65,21 @@ def metrics_golden():
     print("wrote ref_metrics.npz")
 
 
+def train_step_golden():
+    """Training-step golden: loss and parameter updates of ONE reference optimisation step
+    (reference module in train mode + its loss classes + torch.optim.AdamW), probes of six tensors."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_train_oracle import PROBE, reference_train_step
+    ref_loss, ref_sd = reference_train_step("UnrealEgo")
+    sd = weights.make_state_dict("UnrealEgo", seed=WEIGHT_SEED)
+    out = dict(loss=np.float64(ref_loss))
+    for i, k in enumerate(PROBE):
+        out["upd_%d" % i] = (ref_sd[k] - sd[k]).flatten()[:4096].numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_train_step.npz"), **out)
+    print("wrote ref_train_step.npz")
+
+
 if __name__ == "__main__":
     main()
     metrics_golden()
+    train_step_golden()
