@@ -1,0 +1,69 @@
+"""Why the fp32-parity mode issues three MMAs per k-step, checked on the CPU by emulating the
+tensor-core operand roundings inside the oracle: every contraction (linear / matmul / patch conv) sees its operands
+rounded to bf16 (one MMA), or split into bf16 hi + lo with the products Ah*Bh + Ah*Bl + Al*Bh (three MMAs), all
+accumulated in fp32 -- exactly what egotap_b200/csrc/gemm.cuh and attention.cu feed tcgen05.mma.
+
+Expected (and measured on B200, profiles/r01a_parity.jsonl): plain bf16 misses the 1e-3 relative bound by ~10x,
+the split meets it with >4x margin."""
+import contextlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import egotap_oracle as orc
+from egotap_b200.synthetic import synthetic_heatmaps
+
+
+def _hi(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _split(t):
+    h = _hi(t)
+    return h, _hi(t - h)
+
+
+@contextlib.contextmanager
+def emulate(mode):
+    real_linear, real_matmul, real_conv = F.linear, torch.matmul, F.conv2d
+
+    def contract(op, a, b):
+        if mode == "bf16":
+            return op(_hi(a), _hi(b))
+        ah, al = _split(a)
+        bh, bl = _split(b)
+        return op(ah, bh) + op(ah, bl) + op(al, bh)
+
+    def linear(x, w, b=None):
+        y = contract(lambda p, q: real_linear(p, q), x, w)
+        return y if b is None else y + b
+
+    def matmul(a, b):
+        return contract(real_matmul, a, b)
+
+    def conv2d(x, w, b=None, **kw):
+        y = contract(lambda p, q: real_conv(p, q, None, **kw), x, w)
+        return y if b is None else y + b.view(1, -1, 1, 1)
+
+    F.linear, torch.matmul, F.conv2d = linear, matmul, conv2d
+    try:
+        yield
+    finally:
+        F.linear, torch.matmul, F.conv2d = real_linear, real_matmul, real_conv
+
+
+@pytest.mark.parametrize("preset", ["UnrealEgo", "EgoCap"])
+def test_bf16_operands_miss_the_bound_and_the_split_meets_it(preset, state_dicts):
+    sd = state_dicts(preset)
+    x = synthetic_heatmaps(preset, 2, seed=1234, kind="gauss")
+    with torch.no_grad():
+        truth = orc.forward({k: v.double() for k, v in sd.items()}, x.double(), preset)
+        with emulate("bf16"):
+            one = orc.forward(sd, x, preset)
+        with emulate("bf16x3"):
+            three = orc.forward(sd, x, preset)
+    r1, r3 = orc.parity_report(one, truth), orc.parity_report(three, truth)
+    assert r1["rel"] > 2e-3, r1                 # one MMA per k-step: fails 1e-3 (GPU bf16 mode measured 9.7e-3)
+    assert r3["rel"] < 2.5e-4, r3               # three MMAs: passes with margin (GPU measured 2.1e-4 / 5.8e-5)
+    assert r3["mpjpe_delta_mm"] < 0.01 < 0.1
