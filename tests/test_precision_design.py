@@ -31,6 +31,10 @@ def emulate(mode):
     def contract(op, a, b):
         if mode == "bf16":
             return op(_hi(a), _hi(b))
+        if mode == "two_mma":           # the cheapest conceivable 2-MMA scheme: bf16 hi/lo A times an fp16-rounded B
+            ah, al = _split(a)
+            b16 = b.to(torch.float16).to(torch.float32)
+            return op(ah, b16) + op(al, b16)
         ah, al = _split(a)
         bh, bl = _split(b)
         return op(ah, bh) + op(ah, bl) + op(al, bh)
@@ -63,7 +67,10 @@ def test_bf16_operands_miss_the_bound_and_the_split_meets_it(preset, state_dicts
             one = orc.forward(sd, x, preset)
         with emulate("bf16x3"):
             three = orc.forward(sd, x, preset)
+        with emulate("two_mma"):
+            two = orc.forward(sd, x, preset)
     r1, r3 = orc.parity_report(one, truth), orc.parity_report(three, truth)
+    assert orc.parity_report(two, truth)["rel"] > 1e-3      # an 11-bit operand anywhere already breaks the bound
     assert r1["rel"] > 2e-3, r1                 # one MMA per k-step: fails 1e-3 (GPU bf16 mode measured 9.7e-3)
     assert r3["rel"] < 2.5e-4, r3               # three MMAs: passes with margin (GPU measured 2.1e-4 / 5.8e-5)
     assert r3["mpjpe_delta_mm"] < 0.01 < 0.1
