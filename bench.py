@@ -172,7 +172,7 @@ def run_ours(args):
     from egotap_b200 import capi
     from egotap_b200.pipeline import HostPipeline
     from egotap_b200.sharded import gather_poses
-    from ref_shim import make_opt
+    from egotap_b200.options import make_opt
 
     B, K, W = args.batch, args.steps, args.warmup
     torch.manual_seed(0)                                   # reference-style random init (kaiming), same on every rank

@@ -6,6 +6,7 @@ Public surface mirrors the reference's construction seam:
 """
 from .net_architecture import EgoTAPAutoEncoder  # noqa: F401
 from .network import define_AutoEncoder  # noqa: F401
+from .options import make_opt  # noqa: F401
 from .synthetic import synthetic_heatmaps  # noqa: F401
 
-__all__ = ["EgoTAPAutoEncoder", "define_AutoEncoder", "synthetic_heatmaps"]
+__all__ = ["EgoTAPAutoEncoder", "define_AutoEncoder", "make_opt", "synthetic_heatmaps"]

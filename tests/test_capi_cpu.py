@@ -76,6 +76,18 @@ def test_module_surface_matches_reference():
         egotap_b200.define_AutoEncoder(make_opt("UnrealEgo"), "something_else")
 
 
+def test_product_options_helper_matches_the_reference_presets():
+    """egotap_b200.options.make_opt (product side) == the fields the reference parser yields for the two presets
+    (ref_shim.make_opt is the test-side twin used to construct the real reference module)."""
+    import egotap_b200
+    for preset in ("UnrealEgo", "EgoCap"):
+        a, b = vars(egotap_b200.make_opt(preset)), vars(make_opt(preset))
+        for k in b:
+            assert a[k] == b[k], (preset, k)
+    with pytest.raises(ValueError):
+        egotap_b200.make_opt("Nope")
+
+
 def test_factory_inits_like_the_reference(capsys):
     import egotap_b200
     net = egotap_b200.define_AutoEncoder(make_opt("EgoCap"), "egotap_autoencoder")

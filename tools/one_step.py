@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 import egotap_b200  # noqa: E402
-from ref_shim import make_opt  # noqa: E402
+from egotap_b200.options import make_opt  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
