@@ -22,6 +22,14 @@ EXPORTS = [
     "egotap_b200_pu_permute_split", "egotap_b200_pu_chain", "egotap_b200_head", "egotap_b200_pose_metrics", "egotap_b200_profile_begin", "egotap_b200_profile_end", "egotap_b200_profile_record",
     "egotap_b200_num_params", "egotap_b200_param_name", "egotap_b200_plan_sizes", "egotap_b200_plan_create",
     "egotap_b200_plan_destroy", "egotap_b200_pack_weights", "egotap_b200_forward", "egotap_b200_plan_buffer",
+    # training step (csrc/train_ops.cu, csrc/train_model.cu)
+    "egotap_b200_zero", "egotap_b200_copy", "egotap_b200_add3", "egotap_b200_split2d", "egotap_b200_fill_dummy",
+    "egotap_b200_pos_permute", "egotap_b200_pu_bridge_gate", "egotap_b200_transpose_split", "egotap_b200_transpose_bf16",
+    "egotap_b200_colsum", "egotap_b200_reduce_partials", "egotap_b200_gelu_fwd", "egotap_b200_gelu_bwd",
+    "egotap_b200_layernorm_bwd", "egotap_b200_softmax_bwd", "egotap_b200_bn_stats", "egotap_b200_bn_apply",
+    "egotap_b200_bn_bwd", "egotap_b200_regroup_gather", "egotap_b200_pu_cell_fwd", "egotap_b200_pu_cell_bwd",
+    "egotap_b200_pu_bridge_gate_bwd", "egotap_b200_head_bwd", "egotap_b200_embed_grads", "egotap_b200_pose_loss",
+    "egotap_b200_adamw",
 ]
 
 
@@ -47,6 +55,38 @@ class Gemm(C.Structure):
 
 
 _lib = None
+
+
+def _TRAIN_ARGTYPES(P, LL, I, F):
+    """argument types of the training entries, in the order include/egotap_b200.h declares them"""
+    return {
+        "egotap_b200_zero": [P, C.c_size_t, P],
+        "egotap_b200_copy": [P, P, C.c_size_t, P],
+        "egotap_b200_add3": [P, P, P, P, I, P],
+        "egotap_b200_split2d": [P, LL, LL, LL, P, P, LL, P],
+        "egotap_b200_fill_dummy": [P, P, I, I, I, P],
+        "egotap_b200_pos_permute": [P, P, I, I, P, P, P],
+        "egotap_b200_pu_bridge_gate": [P, I, I, P, I, I, LL, P, P, P],
+        "egotap_b200_transpose_split": [P, LL, I, LL, I, I, P, P, LL, P, P, LL, LL, P],
+        "egotap_b200_transpose_bf16": [P, P, LL, I, LL, I, LL, I, LL, P, P, LL, LL, LL, LL, P],
+        "egotap_b200_colsum": [P, LL, I, LL, I, I, P, P, LL, P],
+        "egotap_b200_reduce_partials": [P, I, LL, P, P],
+        "egotap_b200_gelu_fwd": [P, LL, P, P, P],
+        "egotap_b200_gelu_bwd": [P, P, LL, P],
+        "egotap_b200_layernorm_bwd": [P, P, P, LL, I, I, F, P, I, P, P, P, LL, P],
+        "egotap_b200_softmax_bwd": [P, P, LL, I, F, P, P, P, P, P],
+        "egotap_b200_bn_stats": [P, LL, I, P, P, P, P, P, F, F, P, P, P, P, P, LL, P],
+        "egotap_b200_bn_apply": [P, LL, I, P, P, P, P, LL, P, LL, I, I, P],
+        "egotap_b200_bn_bwd": [P, P, LL, I, P, P, P, P, P, P, P, LL, P],
+        "egotap_b200_regroup_gather": [P, LL, I, LL, I, I, P, P],
+        "egotap_b200_pu_cell_fwd": [P, LL, LL, P, LL, LL, P, P, P, P, P, P, I, I, LL, P],
+        "egotap_b200_pu_cell_bwd": [P, LL, LL, P, LL, LL, P, P, P, P, P, P, LL, LL, P, LL, LL, P, P, I, I, LL, P],
+        "egotap_b200_pu_bridge_gate_bwd": [P, LL, P, LL, I, P, I, LL, P, LL, P],
+        "egotap_b200_head_bwd": [P, P, LL, P, P, P, LL, I, P, LL, P, P, P, P, P, P, LL, P],
+        "egotap_b200_embed_grads": [P, I, I, P, P, P],
+        "egotap_b200_pose_loss": [P, P, LL, I, C.POINTER(C.c_int), I, I, F, F, P, P, P, LL, P],
+        "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I, F, F, F, F, F, P],
+    }
 
 
 def lib():
@@ -78,6 +118,9 @@ def lib():
         L.egotap_b200_pack_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         L.egotap_b200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.egotap_b200_plan_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        P, LL, I, F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+        for name, args in _TRAIN_ARGTYPES(P, LL, I, F).items():
+            getattr(L, name).argtypes = args
         _lib = L
     return _lib
 
@@ -229,3 +272,163 @@ def profile_kernels(fn):
 
 def profile_gemms(fn):
     return [r for r in profile_kernels(fn) if "flops" in r]
+
+
+class CudaBackend:
+    """The product backend of ``training.TrainEngine``: every method is ONE call into libegotap_b200.so on the current
+    CUDA stream (same method names and argument meaning as the op oracle used by the tests, oracle/op_oracle.py).
+    Tensors are passed as device pointers (``data_ptr`` of the given view); nothing here computes anything."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        import torch
+        self.L = lib()                                   # raises if the library has not been built
+        if not torch.cuda.is_available():
+            raise RuntimeError("egotap_b200 has no CPU path: the training engine needs a CUDA device")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._preset_of_J = {15: PRESET_ID["UnrealEgo"], 17: PRESET_ID["EgoCap"]}
+
+    @property
+    def launches(self):
+        return self.L.egotap_b200_launch_count()
+
+    @staticmethod
+    def _st():
+        return current_stream()
+
+    # ---- memory
+    def empty(self, shape, dtype=None):
+        import torch
+        return torch.empty(shape, dtype=dtype or torch.float32, device=self.device)
+
+    def zero(self, t):
+        check(self.L.egotap_b200_zero(t.data_ptr(), t.numel() * t.element_size(), self._st()), "zero")
+
+    def copy(self, dst, src):
+        assert dst.numel() == src.numel() and dst.element_size() == src.element_size()
+        check(self.L.egotap_b200_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), self._st()), "copy")
+
+    def add3(self, a, b, c, out, n):
+        check(self.L.egotap_b200_add3(_ptr(a), _ptr(b), _ptr(c), _ptr(out), n, self._st()), "add3")
+
+    # ---- round-1 ops
+    def gemm(self, *a, **k):
+        gemm(*a, **k)
+
+    def split2d(self, src, rows, cols, src_ld, hi, lo, dst_ld):
+        check(self.L.egotap_b200_split2d(_ptr(src), rows, cols, src_ld, _ptr(hi), _ptr(lo), dst_ld, self._st()), "split2d")
+
+    def ingest(self, x, J, p_hi, p_lo, l_hi, l_lo):
+        check(self.L.egotap_b200_ingest(x.data_ptr(), x.shape[0], self._preset_of_J[J], _ptr(p_hi), _ptr(p_lo), _ptr(l_hi),
+                                        _ptr(l_lo), self._st()), "ingest")
+
+    def fill_dummy(self, hidden, dummy, B, tokens, live):
+        if tokens > live:
+            check(self.L.egotap_b200_fill_dummy(_ptr(hidden), _ptr(dummy), B, tokens, live, self._st()), "fill_dummy")
+
+    def pos_permute(self, pos, mask_token, grid, n_hm, pos_perm, dummy):
+        check(self.L.egotap_b200_pos_permute(_ptr(pos), _ptr(mask_token), grid, n_hm, _ptr(pos_perm), _ptr(dummy),
+                                             self._st()), "pos_permute")
+
+    def layernorm(self, x, w, b, frames, rows_in, rows_out, eps, out_hi, out_lo, out_f32):
+        check(self.L.egotap_b200_layernorm(_ptr(x), _ptr(w), _ptr(b), frames, rows_in, rows_out, eps, _ptr(out_hi),
+                                           _ptr(out_lo), _ptr(out_f32), self._st()), "layernorm")
+
+    def attention(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, frames, precision):
+        check(self.L.egotap_b200_attention(_ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
+                                           frames, precision, self._st()), "attention")
+
+    def pu_bridge_gate(self, f, f_ld, f_col, e, e_ld, X, rows, hi, lo):
+        check(self.L.egotap_b200_pu_bridge_gate(_ptr(f), f_ld, f_col, _ptr(e), e_ld, X, rows, _ptr(hi), _ptr(lo), self._st()),
+              "pu_bridge_gate")
+
+    def head(self, e, e_ld, skel, Wp, bp, Wg, bg, frames, J, pose):
+        check(self.L.egotap_b200_head(_ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(bp), _ptr(Wg), _ptr(bg), frames, J, _ptr(pose),
+                                      self._st()), "head")
+
+    # ---- training ops
+    def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows):
+        check(self.L.egotap_b200_transpose_split(_ptr(src), rows, cols, src_ld, rows_in, rows_out, _ptr(rm_hi), _ptr(rm_lo),
+                                                 rm_ld, _ptr(t_hi), _ptr(t_lo), t_ld, pad_rows, self._st()), "transpose_split")
+
+    def transpose_bf16(self, s_hi, s_lo, rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, d_hi, d_lo, d_ld, d_g0s, d_g1s, pad_rows):
+        check(self.L.egotap_b200_transpose_bf16(_ptr(s_hi), _ptr(s_lo), rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, _ptr(d_hi),
+                                                _ptr(d_lo), d_ld, d_g0s, d_g1s, pad_rows, self._st()), "transpose_bf16")
+
+    def colsum(self, src, rows, cols, ld, rows_in, rows_out, out, scratch):
+        check(self.L.egotap_b200_colsum(_ptr(src), rows, cols, ld, rows_in, rows_out, _ptr(out), _ptr(scratch),
+                                        scratch.numel(), self._st()), "colsum")
+
+    def reduce_partials(self, partials, G, n, out):
+        check(self.L.egotap_b200_reduce_partials(_ptr(partials), G, n, _ptr(out), self._st()), "reduce_partials")
+
+    def gelu_fwd(self, u, n, out_hi, out_lo):
+        check(self.L.egotap_b200_gelu_fwd(_ptr(u), n, _ptr(out_hi), _ptr(out_lo), self._st()), "gelu_fwd")
+
+    def gelu_bwd(self, dg, u, n):
+        check(self.L.egotap_b200_gelu_bwd(_ptr(dg), _ptr(u), n, self._st()), "gelu_bwd")
+
+    def layernorm_bwd(self, dy, x, w, frames, rows_in, rows_out, eps, dx, accumulate, dw, db, scratch):
+        check(self.L.egotap_b200_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(w), frames, rows_in, rows_out, eps, _ptr(dx),
+                                               int(accumulate), _ptr(dw), _ptr(db), _ptr(scratch), scratch.numel(),
+                                               self._st()), "layernorm_bwd")
+
+    def softmax_bwd(self, S, dP, rows, cols, scale, p_hi, p_lo, ds_hi, ds_lo):
+        check(self.L.egotap_b200_softmax_bwd(_ptr(S), _ptr(dP), rows, cols, scale, _ptr(p_hi), _ptr(p_lo), _ptr(ds_hi),
+                                             _ptr(ds_lo), self._st()), "softmax_bwd")
+
+    def bn_stats(self, y, rows, cols, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, mean, rstd,
+                 scale, shift, scratch):
+        check(self.L.egotap_b200_bn_stats(_ptr(y), rows, cols, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                          _ptr(num_batches_tracked), momentum, eps, _ptr(mean), _ptr(rstd), _ptr(scale),
+                                          _ptr(shift), _ptr(scratch), scratch.numel(), self._st()), "bn_stats")
+
+    def bn_apply(self, y, rows, cols, scale, shift, out_hi, out_lo, out_ld, out_f32, f32_ld, J, col_off):
+        check(self.L.egotap_b200_bn_apply(_ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(out_hi), _ptr(out_lo), out_ld,
+                                          _ptr(out_f32), f32_ld, J, col_off, self._st()), "bn_apply")
+
+    def bn_bwd(self, da, y, rows, cols, scale, shift, mean, rstd, dgamma, dbeta, scratch):
+        check(self.L.egotap_b200_bn_bwd(_ptr(da), _ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                        _ptr(dgamma), _ptr(dbeta), _ptr(scratch), scratch.numel(), self._st()), "bn_bwd")
+
+    def regroup_gather(self, dE, e_ld, col_off, frames, J, cols, out):
+        check(self.L.egotap_b200_regroup_gather(_ptr(dE), e_ld, col_off, frames, J, cols, _ptr(out), self._st()),
+              "regroup_gather")
+
+    def pu_cell_fwd(self, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, h_hi, h_lo, hg_hi, hg_lo, t, J, B):
+        check(self.L.egotap_b200_pu_cell_fwd(_ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(h_hi),
+                                             _ptr(h_lo), _ptr(hg_hi), _ptr(hg_lo), t, J, B, self._st()), "pu_cell_fwd")
+
+    def pu_cell_bwd(self, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, dOut, dhg, dc, dG, dg_rs, dg_ts, dF, df_rs, df_ts, dgp_hi,
+                    dgp_lo, t, J, B):
+        check(self.L.egotap_b200_pu_cell_bwd(_ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(dOut),
+                                             _ptr(dhg), _ptr(dc), _ptr(dG), dg_rs, dg_ts, _ptr(dF), df_rs, df_ts, _ptr(dgp_hi),
+                                             _ptr(dgp_lo), t, J, B, self._st()), "pu_cell_bwd")
+
+    def pu_bridge_gate_bwd(self, dE, e_ld, F0, f_ld, f_col, E, X, rows, dF, df_ld):
+        check(self.L.egotap_b200_pu_bridge_gate_bwd(_ptr(dE), e_ld, _ptr(F0), f_ld, f_col, _ptr(E), X, rows, _ptr(dF), df_ld,
+                                                    self._st()), "pu_bridge_gate_bwd")
+
+    def head_bwd(self, dpose, e, e_ld, skel, Wp, Wg, frames, J, dE, de_ld, dSkel, dWp, dbp, dWg, dbg, scratch):
+        check(self.L.egotap_b200_head_bwd(_ptr(dpose), _ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(Wg), frames, J, _ptr(dE), de_ld,
+                                          _ptr(dSkel), _ptr(dWp), _ptr(dbp), _ptr(dWg), _ptr(dbg), _ptr(scratch),
+                                          scratch.numel(), self._st()), "head_bwd")
+
+    def embed_grads(self, dpos_perm, grid, n_hm, dpos, dmask):
+        check(self.L.egotap_b200_embed_grads(_ptr(dpos_perm), grid, n_hm, _ptr(dpos), _ptr(dmask), self._st()), "embed_grads")
+
+    def pose_loss(self, pred, gt, frames, nj, parents, drop_first, lambda_mpjpe, lambda_cos, loss, dpose, scratch=None):
+        arr = (C.c_int * len(parents))(*parents)
+        if scratch is None:
+            scratch = self.empty((2 * frames + 64,))
+        check(self.L.egotap_b200_pose_loss(_ptr(pred), _ptr(gt), frames, nj, arr, len(parents), int(drop_first), lambda_mpjpe,
+                                           lambda_cos, _ptr(loss), _ptr(dpose), _ptr(scratch), scratch.numel(), self._st()),
+              "pose_loss")
+
+    def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay):
+        n = len(params)
+        mk = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        numel = (C.c_longlong * n)(*[p.numel() for p in params])
+        check(self.L.egotap_b200_adamw(mk(params), mk(grads), mk(m), mk(v), numel, n, step, lr, beta1, beta2, eps, weight_decay,
+                                       self._st()), "adamw")

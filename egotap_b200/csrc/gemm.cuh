@@ -55,22 +55,6 @@ struct GemmShape {
   int b_shared;     // 1: every group multiplies the same B matrix (B's group coordinates stay 0)
 };
 
-// Exact-erf GELU, x * Phi(x), branch-free: Phi through the complementary error function of |x|/sqrt(2) in the
-// Abramowitz-Stegun 7.1.26 form (|erf error| <= 1.5e-7, i.e. fp32 rounding level; measured max |gelu error| 4.2e-7
-// over [-12, 12] against fp64, the same as an fp32 evaluation of 0.5*x*(1+erf(x/sqrt 2))).  Two MUFU + ~12 FMA-pipe
-// instructions and no divergence, vs. the two-branch libdevice erff.  Reference: ACT2FN['gelu'], modeling_vit.py:326.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = p * t * ex2_approx(u * (u * -1.4426950408889634f));   // erfc(u)
-  const float phi = x < 0.f ? 0.5f * y : fmaf(-0.5f, y, 1.0f);
-  return x * phi;
-}
-
 // Per-thread row mapping of the epilogue (computed once per tile): output row, residual row, column shift.
 struct EpiRow {
   long long orow, rrow;

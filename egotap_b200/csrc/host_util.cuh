@@ -1,5 +1,8 @@
 // Host-side helpers: error plumbing, TMA descriptor creation, launch accounting.
 #pragma once
+#ifdef EB_HOST_EMU
+#include "cuda_emu.h"
+#endif
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
@@ -42,6 +45,22 @@ inline std::atomic<long long>& launch_counter() {
     eb::launch_counter().fetch_add(1, std::memory_order_relaxed);                               \
   } while (0)
 
+// Kernel launch.  EB_LAUNCH_COOP marks kernels whose threads communicate inside a CTA (__syncthreads, warp shuffles,
+// shared-memory atomics); EB_LAUNCH kernels have fully independent threads.  Both are the plain <<<>>> launch here --
+// the distinction only matters to the CUDA-on-CPU emulation the tests build with -DEB_HOST_EMU (tests/cuda_emu), which
+// runs independent-thread kernels as a loop and cooperative ones on fibers.
+#ifdef EB_HOST_EMU
+#define EB_LAUNCH(kernel, grid, block, stream, ...) \
+  eb_emu::launch(dim3(grid), dim3(block), false, [=]() { kernel(__VA_ARGS__); })
+#define EB_LAUNCH_COOP(kernel, grid, block, stream, ...) \
+  eb_emu::launch(dim3(grid), dim3(block), true, [=]() { kernel(__VA_ARGS__); })
+#undef EB_CHECK_LAUNCH
+#define EB_CHECK_LAUNCH(name) eb::launch_counter().fetch_add(1, std::memory_order_relaxed)
+#else
+#define EB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define EB_LAUNCH_COOP(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
+
 #define EB_REQUIRE(cond, ...)                                   \
   do {                                                          \
     if (!(cond)) return eb::fail(EGOTAP_E_ARG, __VA_ARGS__);    \
@@ -60,6 +79,9 @@ struct ProfScope {
   ProfRec r;
   cudaStream_t st;
   bool on;
+#ifdef EB_HOST_EMU
+  ProfScope(const char*, cudaStream_t stream, int = 0, int = 0, int = 0, int = 0, int = -1) : st(stream), on(false) {}
+#else
   ProfScope(const char* name, cudaStream_t stream, int M = 0, int N = 0, int K = 0, int groups = 0, int variant = -1)
       : st(stream), on(prof_on()) {
     if (!on) return;
@@ -68,6 +90,7 @@ struct ProfScope {
     cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
   }
+#endif
   ~ProfScope() {
     if (!on) return;
     cudaEventRecord(r.e1, st);

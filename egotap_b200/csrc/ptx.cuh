@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <cstdio>
 
+#include "numeric.cuh"
+
 namespace eb {
 
 // ---------------------------------------------------------------------------------------------
@@ -224,37 +226,5 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------
-// bf16 hi/lo split (error-compensated operands): x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
-}
-// two floats -> packed bf16x2 (x0 in the low half), round to nearest even: one F2FP instruction
-__device__ __forceinline__ uint32_t cvt_bf16x2(float x0, float x1) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
-  return d;
-}
-// packed hi/lo split of two floats: 6 instructions per pair
-__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_bf16x2(x0, x1);
-  lo = cvt_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
-}
-__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2, 2 ulp
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 }  // namespace eb

@@ -410,7 +410,7 @@ class TrainEngine:
         B = self.batch
         drop_first = not self.global_head
         self.be.pose_loss(self.A["pose"], gt, B, self.nj, KINEMATIC_PARENTS[self.preset], drop_first,
-                          self.lambda_mpjpe, self.lambda_cos_sim, self.loss, self.S["dpose"])
+                          self.lambda_mpjpe, self.lambda_cos_sim, self.loss, self.S["dpose"], self.scr)
         return self.loss
 
     # ------------------------------------------------------------------------------------------ backward

@@ -173,6 +173,84 @@ int egotap_b200_forward(egotap_plan* plan, const float* heatmaps, int batch, flo
 /* device pointer of a named intermediate ("hidden", "fin_hi", "fin_lo", "embed", "h0", "skel") for the parity tests */
 int egotap_b200_plan_buffer(egotap_plan* plan, const char* name, void** ptr);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step: the ops egotap_b200/training.py composes, together with the
+ * GEMM / attention / layernorm / ingest / head entries above, into the train-mode forward, the loss, the full
+ * backward and AdamW.  Replaces what torch.autograd + torch.optim.AdamW do for net_AutoEncoder in the reference's
+ * optimize_parameters (model/egotap_autoencoder_model.py:284-323, model/network.py:72-78, utils/loss.py:44-85,
+ * model/network_utils.py:123-142 for train-mode BatchNorm1d).  Exact semantics of each entry: oracle/op_oracle.py.
+ * `scratch` is a caller-provided fp32 device buffer of `scratch_elems` elements (8-byte aligned) for the
+ * deterministic two-stage reductions.  Pointers named *_host are HOST arrays.
+ * ------------------------------------------------------------------------------------------ */
+int egotap_b200_zero(void* ptr, size_t bytes, void* stream);
+int egotap_b200_copy(void* dst, const void* src, size_t bytes, void* stream);
+int egotap_b200_add3(const float* a, const float* b, const float* c /*nullable*/, float* out, int n, void* stream);
+/* weight / operand preparation (exports of the packing kernels egotap_b200_pack_weights uses) */
+int egotap_b200_split2d(const float* src, long long rows, long long cols, long long src_ld, void* hi, void* lo,
+                        long long dst_ld, void* stream);
+int egotap_b200_fill_dummy(float* hidden, const float* dummy, int frames, int tokens, int live, void* stream);
+int egotap_b200_pos_permute(const float* pos, const float* mask_token, int grid, int n_hm, float* pos_perm, float* dummy,
+                            void* stream);
+int egotap_b200_pu_bridge_gate(const float* f, int f_ld, int f_col, const float* e, int e_ld, int X, long long rows, void* hi,
+                               void* lo, void* stream);
+/* fp32 (rows x cols) -> row-major bf16 pair rm[r][c] and / or transposed pair t[c][r] (t[c][rows..pad_rows) = 0);
+ * logical row r is read from source row (r / rows_out) * rows_in + r % rows_out when rows_out > 0 */
+int egotap_b200_transpose_split(const float* src, long long rows, int cols, long long src_ld, int rows_in, int rows_out,
+                                void* rm_hi, void* rm_lo, long long rm_ld, void* t_hi, void* t_lo, long long t_ld,
+                                long long pad_rows, void* stream);
+/* batched bf16 transpose d[g1][g0][c][r] = s[g1][g0][r][c], zero padded to pad_rows */
+int egotap_b200_transpose_bf16(const void* s_hi, const void* s_lo, long long rows, int cols, long long s_ld, int g0_count,
+                               long long s_g0_stride, int g1_count, long long s_g1_stride, void* d_hi, void* d_lo,
+                               long long d_ld, long long d_g0_stride, long long d_g1_stride, long long pad_rows, void* stream);
+/* out[c] = sum_r src[row(r)][c]  (bias gradients; per-token sums over frames) */
+int egotap_b200_colsum(const float* src, long long rows, int cols, long long ld, int rows_in, int rows_out, float* out,
+                       float* scratch, long long scratch_elems, void* stream);
+/* out[i] = sum_g partials[g*n + i]  (split-K partial products of the dW GEMMs) */
+int egotap_b200_reduce_partials(const float* partials, int G, long long n, float* out, void* stream);
+int egotap_b200_gelu_fwd(const float* u, long long n, void* out_hi, void* out_lo, void* stream);
+int egotap_b200_gelu_bwd(float* dg /*in place*/, const float* u, long long n, void* stream);
+int egotap_b200_layernorm_bwd(const float* dy, const float* x, const float* w, long long frames, int rows_in, int rows_out,
+                              float eps, float* dx, int accumulate, float* dw, float* db, float* scratch,
+                              long long scratch_elems, void* stream);
+/* P = softmax(S) ; dS = P * (dP - rowsum(P * dP)) * scale ; S, dP fp32 (rows x 576) */
+int egotap_b200_softmax_bwd(const float* S, const float* dP, long long rows, int cols, float scale, void* p_hi, void* p_lo,
+                            void* ds_hi, void* ds_lo, void* stream);
+/* train-mode BatchNorm1d: batch statistics + running-buffer update + folded scale/shift; apply with LeakyReLU(0.2)
+ * (optionally into the per-joint [left | right] layout); backward through LeakyReLU and the batch statistics */
+int egotap_b200_bn_stats(const float* y, long long rows, int cols, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, long long* num_batches_tracked /*nullable, device*/, float momentum, float eps,
+                         float* mean, float* rstd, float* scale, float* shift, float* scratch, long long scratch_elems,
+                         void* stream);
+int egotap_b200_bn_apply(const float* y, long long rows, int cols, const float* scale, const float* shift, void* out_hi,
+                         void* out_lo, long long out_ld, float* out_f32, long long f32_ld, int J, int col_off, void* stream);
+int egotap_b200_bn_bwd(float* da /*in place -> dy*/, const float* y, long long rows, int cols, const float* scale,
+                       const float* shift, const float* mean, const float* rstd, float* dgamma, float* dbeta, float* scratch,
+                       long long scratch_elems, void* stream);
+int egotap_b200_regroup_gather(const float* dE, long long e_ld, int col_off, long long frames, int J, int cols, float* out,
+                               void* stream);
+/* propagation-unit cell, one joint step, with the cell / hidden state of every step kept for the backward
+ * (reference model/custom_cells.py:94-120), and its backward (BPTT, t = J-1 .. 0) */
+int egotap_b200_pu_cell_fwd(const float* G, long long g_rs, long long g_ts, const float* F, long long f_rs, long long f_ts,
+                            float* C, float* H, void* h_hi, void* h_lo, void* hg_hi, void* hg_lo, int t, int J,
+                            long long frames, void* stream);
+int egotap_b200_pu_cell_bwd(const float* G, long long g_rs, long long g_ts, const float* F, long long f_rs, long long f_ts,
+                            const float* C, const float* H, const float* dOut, const float* dhg, float* dc, float* dG,
+                            long long dg_rs, long long dg_ts, float* dF, long long df_rs, long long df_ts, void* dgp_hi,
+                            void* dgp_lo, int t, int J, long long frames, void* stream);
+int egotap_b200_pu_bridge_gate_bwd(float* dE, long long e_ld, const float* F0, long long f_ld, int f_col, const float* E, int X,
+                                   long long rows, float* dF, long long df_ld, void* stream);
+int egotap_b200_head_bwd(const float* dpose, const float* e, long long e_ld, const float* skel, const float* Wp,
+                         const float* Wg /*nullable*/, long long frames, int J, float* dE, long long de_ld, float* dSkel,
+                         float* dWp, float* dbp, float* dWg, float* dbg, float* scratch, long long scratch_elems, void* stream);
+int egotap_b200_embed_grads(const float* dpos_perm, int grid, int n_hm, float* dpos, float* dmask, void* stream);
+/* loss[0] = total, [1] = lambda_mpjpe * MPJPE, [2] = lambda_cos * lambda_mpjpe * bone cosine; dpose = d total / d pred */
+int egotap_b200_pose_loss(const float* pred, const float* gt, long long frames, int joints, const int* parents_host,
+                          int n_parents, int drop_first, float lambda_mpjpe, float lambda_cos, float* loss, float* dpose,
+                          float* scratch, long long scratch_elems, void* stream);
+int egotap_b200_adamw(float* const* params_host, const float* const* grads_host, float* const* m_host, float* const* v_host,
+                      const long long* numel_host, int count, int step, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -513,7 +513,7 @@ class OracleBackend:
         flat(dpos)[:576 * 1024] = out.reshape(-1)
         flat(dmask)[:1024] = d[n_hm * 16:].sum(0)
 
-    def pose_loss(self, pred, gt, frames, nj, parents, drop_first, lambda_mpjpe, lambda_cos, loss, dpose):
+    def pose_loss(self, pred, gt, frames, nj, parents, drop_first, lambda_mpjpe, lambda_cos, loss, dpose, scratch=None):
         """loss[0] = total, loss[1] = mpjpe term, loss[2] = cos-sim term (reference
         model/egotap_autoencoder_model.py:284-296, utils/loss.py:44-85); dpose = d total / d pred.
         parents: kinematic parents over the (possibly root-prepended) joint list; drop_first: EgoCap prepends a zero

@@ -99,3 +99,72 @@ def test_factory_inits_like_the_reference(capsys):
     assert sd["pos_heatmap_encoder.fc1.fc.bias"].abs().max() == 0
     assert sd["pos_heatmap_encoder.fc1.bn.running_var"].min() == 1
     assert abs(sd["pos_heatmap_encoder.vit.embeddings.position_embeddings"].std().item() - 0.02) < 1e-3   # trunc-normal(0.02)
+
+
+def _header_prototypes():
+    """name -> list of C parameter type strings, parsed from include/egotap_b200.h"""
+    header = open(os.path.join(ROOT, "include", "egotap_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(egotap_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if args == ["void"] else args
+    return protos
+
+
+def _ctype_class(decl):
+    """coarse class of a C parameter declaration: 'ptr', 'int', 'll', 'size', 'float'"""
+    if "*" in decl:
+        return "ptr"
+    for key, cls in (("size_t", "size"), ("long long", "ll"), ("float", "float"), ("int", "int")):
+        if decl.startswith(key) or (" " + key + " ") in (" " + decl):
+            return cls
+    raise AssertionError("unparsed parameter declaration %r" % decl)
+
+
+def test_ctypes_signatures_match_the_header(lib):
+    """every entry that has ctypes argtypes: same arity and the same coarse type class per position as the header --
+    a swapped or missing argument in the binding would otherwise only show up on the GPU"""
+    import ctypes as C
+    protos = _header_prototypes()
+    cls_of = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "int", C.c_longlong: "ll", C.c_size_t: "size", C.c_float: "float"}
+    checked = 0
+    for name, params in protos.items():
+        argtypes = getattr(lib, name).argtypes
+        if argtypes is None:
+            continue
+        assert len(argtypes) == len(params), (name, len(argtypes), len(params))
+        for i, (t, decl) in enumerate(zip(argtypes, params)):
+            got = cls_of.get(t, "ptr")           # POINTER(...) types
+            want = _ctype_class(decl)
+            if want == "size" and got == "ll":
+                continue
+            assert got == want, (name, i, decl, t)
+        checked += 1
+    assert checked >= 40
+
+
+def test_training_entries_reject_bad_arguments_without_a_gpu(lib):
+    """argument validation runs before any CUDA call, so the marshalling order of the training entries can be probed on
+    the CPU: a deliberately bad value in ONE position must produce the error that names it"""
+    import ctypes as C
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    err = lambda: lib.egotap_b200_last_error().decode()
+    assert lib.egotap_b200_transpose_split(p, 128, 65, 128, 0, 0, p, p, 128, None, None, 0, 0, None) < 0 and "cols (65)" in err()
+    assert lib.egotap_b200_transpose_split(p, 128, 64, 64, 0, 0, None, None, 0, p, p, 130, 100, None) < 0 and "rows 128 pad 100 ld 130" in err()
+    assert lib.egotap_b200_transpose_bf16(p, p, 10, 70, 128, 1, 0, 1, 0, p, p, 64, 0, 0, 64, None) < 0 and "cols (70)" in err()
+    assert lib.egotap_b200_transpose_bf16(p, p, 10, 64, 128, 1, 0, 1, 0, p, p, 20, 0, 0, 8, None) < 0 and "rows 10 pad 8 ld 20" in err()
+    assert lib.egotap_b200_colsum(p, 16, 6, 8, 0, 0, p, p, 64, None) < 0 and "multiples of 4" in err()
+    assert lib.egotap_b200_reduce_partials(p, 2, 6, p, None) < 0 and "G 2 n 6" in err()
+    assert lib.egotap_b200_softmax_bwd(p, p, 8, 512, 1.0, p, p, p, p, None) < 0 and "got 512" in err()
+    assert lib.egotap_b200_layernorm_bwd(p, p, p, 1, 576, 600, 1e-12, p, 0, p, p, p, 64, None) < 0 and "rows_out" in err()
+    assert lib.egotap_b200_bn_apply(p, 31, 128, p, p, p, p, 128, None, 0, 15, 0, None) < 0 and "rows (31)" in err()
+    assert lib.egotap_b200_pu_cell_fwd(p, 2048, 2048, p, 768, 768, p, p, None, None, p, p, 15, 15, 4, None) < 0 and "step 15 of 15" in err()
+    assert lib.egotap_b200_pu_cell_bwd(p, 2048, 2048, p, 768, 768, p, p, p, p, p, p, 2048, 2048, p, 768, 770, p, p, 0, 15, 4, None) < 0 \
+        and "strides" in err()
+    parents = (C.c_int * 16)(*[0, 0, 1, 1, 2, 3, 4, 5, 2, 3, 8, 9, 10, 11, 12, 13])
+    assert lib.egotap_b200_pose_loss(p, p, 4, 16, parents, 15, 0, 0.1, -0.01, p, p, p, 64, None) < 0 and "16 joints / 15 parents" in err()
+    assert lib.egotap_b200_head_bwd(p, p, 512, p, p, p, 4, 15, p, 512, p, p, p, None, None, p, 64, None) < 0 and "dWg" in err()
+    assert lib.egotap_b200_embed_grads(p, 5, 30, p, p, None) < 0 and "geometry" in err()
+    assert lib.egotap_b200_regroup_gather(p, 512, 2, 4, 15, 128, p, None) < 0 and "multiples of 4" in err()
