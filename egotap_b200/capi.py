@@ -85,7 +85,7 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_head_bwd": [P, P, LL, P, P, P, LL, I, P, LL, P, P, P, P, P, P, LL, P],
         "egotap_b200_embed_grads": [P, I, I, P, P, P],
         "egotap_b200_pose_loss": [P, P, LL, I, C.POINTER(C.c_int), I, I, F, F, P, P, P, LL, P],
-        "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I, F, F, F, F, F, P],
+        "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I] + [C.c_double] * 5 + [P],
     }
 
 

@@ -558,19 +558,18 @@ struct AdamTable {
   long long n[64];
 };
 
-__global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float lr, float beta1, float beta2, float eps,
-                                                    float weight_decay, float inv_bc1, float inv_sqrt_bc2) {
+__global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, float beta1, float omb1, float beta2,
+                                                    float omb2, float step, float inv_sqrt_bc2, float eps) {
   const int k = blockIdx.y;
   float* __restrict__ p = tab.p[k];
   const float* __restrict__ g = tab.g[k];
   float* __restrict__ m = tab.m[k];
   float* __restrict__ v = tab.v[k];
   const long long n = tab.n[k];
-  const float decay = 1.0f - lr * weight_decay, step = lr * inv_bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i];
-    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float mi = beta1 * m[i] + omb1 * gi;
+    const float vi = beta2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     p[i] = p[i] * decay - step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
@@ -578,9 +577,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float lr, flo
 }
 
 int adamw_run(float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, int count, int step,
-              float lr, float beta1, float beta2, float eps, float weight_decay, cudaStream_t st) {
+              double lr, double beta1, double beta2, double eps, double weight_decay, cudaStream_t st) {
   EB_REQUIRE(p && g && m && v && n && count > 0 && step >= 1, "adamw: bad arguments");
-  const double bc1 = 1.0 - pow(double(beta1), double(step)), bc2 = 1.0 - pow(double(beta2), double(step));
+  // hyper-parameters arrive in double, as torch.optim.AdamW holds them; every derived constant is formed in double
+  // and rounded to fp32 once (1 - beta2 formed in fp32 would be off by 5e-5 relative)
+  const double bc1 = 1.0 - pow(beta1, double(step)), bc2 = 1.0 - pow(beta2, double(step));
   for (int base = 0; base < count; base += 64) {
     AdamTable tab;
     memset(&tab, 0, sizeof(tab));
@@ -592,8 +593,9 @@ int adamw_run(float* const* p, const float* const* g, float* const* m, float* co
       if (n[base + i] > biggest) biggest = n[base + i];
     }
     ProfScope prof("adamw_kernel", st);
-    EB_LAUNCH(adamw_kernel, dim3(blocks_for(biggest, 256 * 8, 148 * 2), cnt), 256, st, tab, lr, beta1, beta2, eps, weight_decay,
-              float(1.0 / bc1), float(1.0 / sqrt(bc2)));
+    EB_LAUNCH(adamw_kernel, dim3(blocks_for(biggest, 256 * 8, 148 * 2), cnt), 256, st, tab, float(1.0 - lr * weight_decay),
+              float(beta1), float(1.0 - beta1), float(beta2), float(1.0 - beta2), float(lr / bc1), float(1.0 / sqrt(bc2)),
+              float(eps));
     EB_CHECK_LAUNCH("adamw_kernel");
   }
   return 0;
@@ -675,8 +677,8 @@ extern "C" int egotap_b200_pose_loss(const float* pred, const float* gt, long lo
                        scratch, scratch_elems, (cudaStream_t)stream);
 }
 extern "C" int egotap_b200_adamw(float* const* params_host, const float* const* grads_host, float* const* m_host,
-                                 float* const* v_host, const long long* numel_host, int count, int step, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, void* stream) {
+                                 float* const* v_host, const long long* numel_host, int count, int step, double lr, double beta1,
+                                 double beta2, double eps, double weight_decay, void* stream) {
   return adamw_run(params_host, grads_host, m_host, v_host, numel_host, count, step, lr, beta1, beta2, eps, weight_decay,
                    (cudaStream_t)stream);
 }

@@ -248,8 +248,8 @@ int egotap_b200_pose_loss(const float* pred, const float* gt, long long frames, 
                           int n_parents, int drop_first, float lambda_mpjpe, float lambda_cos, float* loss, float* dpose,
                           float* scratch, long long scratch_elems, void* stream);
 int egotap_b200_adamw(float* const* params_host, const float* const* grads_host, float* const* m_host, float* const* v_host,
-                      const long long* numel_host, int count, int step, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, void* stream);
+                      const long long* numel_host, int count, int step, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

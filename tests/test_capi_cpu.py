@@ -116,7 +116,7 @@ def _ctype_class(decl):
     """coarse class of a C parameter declaration: 'ptr', 'int', 'll', 'size', 'float'"""
     if "*" in decl:
         return "ptr"
-    for key, cls in (("size_t", "size"), ("long long", "ll"), ("float", "float"), ("int", "int")):
+    for key, cls in (("size_t", "size"), ("long long", "ll"), ("double", "double"), ("float", "float"), ("int", "int")):
         if decl.startswith(key) or (" " + key + " ") in (" " + decl):
             return cls
     raise AssertionError("unparsed parameter declaration %r" % decl)
@@ -127,7 +127,7 @@ def test_ctypes_signatures_match_the_header(lib):
     a swapped or missing argument in the binding would otherwise only show up on the GPU"""
     import ctypes as C
     protos = _header_prototypes()
-    cls_of = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "int", C.c_longlong: "ll", C.c_size_t: "size", C.c_float: "float"}
+    cls_of = {C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_int: "int", C.c_longlong: "ll", C.c_size_t: "size", C.c_float: "float", C.c_double: "double"}
     checked = 0
     for name, params in protos.items():
         argtypes = getattr(lib, name).argtypes
