@@ -85,7 +85,7 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_head_bwd": [P, P, LL, P, P, P, LL, I, P, LL, P, P, P, P, P, P, LL, P],
         "egotap_b200_embed_grads": [P, I, I, P, P, P],
         "egotap_b200_pose_loss": [P, P, LL, I, C.POINTER(C.c_int), I, I, F, F, P, P, P, LL, P],
-        "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I] + [C.c_double] * 5 + [P],
+        "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I] + [C.c_double] * 6 + [P],
     }
 
 
@@ -426,9 +426,9 @@ class CudaBackend:
                                            lambda_cos, _ptr(loss), _ptr(dpose), _ptr(scratch), scratch.numel(), self._st()),
               "pose_loss")
 
-    def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay):
+    def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
         n = len(params)
         mk = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
         numel = (C.c_longlong * n)(*[p.numel() for p in params])
         check(self.L.egotap_b200_adamw(mk(params), mk(grads), mk(m), mk(v), numel, n, step, lr, beta1, beta2, eps, weight_decay,
-                                       self._st()), "adamw")
+                                       grad_scale, self._st()), "adamw")

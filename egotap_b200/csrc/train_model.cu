@@ -559,7 +559,7 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, float beta1, float omb1, float beta2,
-                                                    float omb2, float step, float inv_sqrt_bc2, float eps) {
+                                                    float omb2, float step, float inv_sqrt_bc2, float eps, float grad_scale) {
   const int k = blockIdx.y;
   float* __restrict__ p = tab.p[k];
   const float* __restrict__ g = tab.g[k];
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, 
   float* __restrict__ v = tab.v[k];
   const long long n = tab.n[k];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i];
+    const float gi = g[i] * grad_scale;
     const float mi = beta1 * m[i] + omb1 * gi;
     const float vi = beta2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, 
 }
 
 int adamw_run(float* const* p, const float* const* g, float* const* m, float* const* v, const long long* n, int count, int step,
-              double lr, double beta1, double beta2, double eps, double weight_decay, cudaStream_t st) {
+              double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale, cudaStream_t st) {
   EB_REQUIRE(p && g && m && v && n && count > 0 && step >= 1, "adamw: bad arguments");
   // hyper-parameters arrive in double, as torch.optim.AdamW holds them; every derived constant is formed in double
   // and rounded to fp32 once (1 - beta2 formed in fp32 would be off by 5e-5 relative)
@@ -595,7 +595,7 @@ int adamw_run(float* const* p, const float* const* g, float* const* m, float* co
     ProfScope prof("adamw_kernel", st);
     EB_LAUNCH(adamw_kernel, dim3(blocks_for(biggest, 256 * 8, 148 * 2), cnt), 256, st, tab, float(1.0 - lr * weight_decay),
               float(beta1), float(1.0 - beta1), float(beta2), float(1.0 - beta2), float(lr / bc1), float(1.0 / sqrt(bc2)),
-              float(eps));
+              float(eps), float(grad_scale));
     EB_CHECK_LAUNCH("adamw_kernel");
   }
   return 0;
@@ -678,7 +678,7 @@ extern "C" int egotap_b200_pose_loss(const float* pred, const float* gt, long lo
 }
 extern "C" int egotap_b200_adamw(float* const* params_host, const float* const* grads_host, float* const* m_host,
                                  float* const* v_host, const long long* numel_host, int count, int step, double lr, double beta1,
-                                 double beta2, double eps, double weight_decay, void* stream) {
+                                 double beta2, double eps, double weight_decay, double grad_scale, void* stream) {
   return adamw_run(params_host, grads_host, m_host, v_host, numel_host, count, step, lr, beta1, beta2, eps, weight_decay,
-                   (cudaStream_t)stream);
+                   grad_scale, (cudaStream_t)stream);
 }

@@ -87,6 +87,40 @@ def _register(root, key, tensor, is_buffer):
         m.register_parameter(parts[-1], nn.Parameter(tensor))
 
 
+class _LiftTrainFn(torch.autograd.Function):
+    """The autograd seam of train mode: forward / backward are the CUDA training engine (egotap_b200/training.py), so
+    the reference's own loop -- loss in torch, ``scaler.scale(loss).backward()``, ``torch.optim.AdamW.step()``
+    (reference model/egotap_autoencoder_model.py:299-323) -- works unchanged on this module."""
+
+    @staticmethod
+    def forward(ctx, x, module, names, *params):
+        eng = module._engine
+        eng.packed = False              # an external optimiser may have updated the parameters since the last step
+        pose = eng.forward(x)
+        out = eng.be.empty(tuple(pose.shape), torch.float32)
+        eng.be.copy(out, pose)          # the engine's pose buffer is reused by the next step
+        ctx.module, ctx.names = module, names
+        return out
+
+    @staticmethod
+    def backward(ctx, dpose):
+        eng = ctx.module._engine
+        d = dpose.contiguous()
+        if d.dtype != torch.float32:
+            d = d.float()
+        grads = eng.backward(d)
+        out = []
+        for n in ctx.names:             # fresh tensors: autograd may keep them as .grad, the flat buffer is reused
+            g = grads.get(n)
+            if g is None:
+                out.append(None)
+                continue
+            c = eng.be.empty(tuple(g.shape), torch.float32)
+            eng.be.copy(c, g)
+            out.append(c)
+        return (None, None, None) + tuple(out)
+
+
 class EgoTAPAutoEncoder(nn.Module):
     """B200-native drop-in for reference ``EgoTAPAutoEncoder`` (model/net_architecture.py:579-758).
 
@@ -146,6 +180,8 @@ class EgoTAPAutoEncoder(nn.Module):
         self._plan_key = None
         self._packed_versions = None
         self._zeros = {}
+        self._engine = None
+        self._engine_backend = None      # tests inject the op oracle here; the product default is the CUDA library
         self.skel_inputs = None
         self.skel_embed = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -180,6 +216,7 @@ class EgoTAPAutoEncoder(nn.Module):
         self._plan = None
         self._packed_versions = None
         self._zeros = {}
+        self._engine = None
         return r
 
     def _ensure_plan(self, batch, device):
@@ -232,12 +269,44 @@ class EgoTAPAutoEncoder(nn.Module):
         self._packed_versions = versions
 
     # ------------------------------------------------------------------ forward
+    # ------------------------------------------------------------------ train mode
+    def train_engine(self):
+        """The training engine bound to this module's parameters and BatchNorm buffers (created on first use)."""
+        if self._engine is None:
+            from .training import TrainEngine
+            tensors = {k: v.data for k, v in self.named_parameters()}
+            tensors.update({k: v for k, v in self.named_buffers()})
+            precision = "bf16" if self._precision == capi.PREC_BF16 else "bf16x3"
+            self._engine = TrainEngine(self.joint_preset, tensors, precision=precision, backend=self._engine_backend)
+        return self._engine
+
+    def _run_train(self, input):
+        """train-mode forward (BatchNorm1d batch statistics, running buffers updated) with an autograd graph to
+        every trained parameter (reference: the same nn.Module under .train(), model/network_utils.py:123-142)"""
+        if self._engine_backend is None and not input.is_cuda:
+            raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
+        assert input.dim() == 4 and input.size(1) == self.channels_heatmap and input.size(2) == self.W and input.size(3) == self.H, \
+            "expected (B, %d, %d, %d) heatmaps, got %s" % (self.channels_heatmap, self.W, self.H, tuple(input.shape))
+        x = input.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        eng = self.train_engine()
+        names = [k for k in eng.order]
+        params = dict(self.named_parameters())
+        if torch.is_grad_enabled() and any(params[n].requires_grad for n in names):
+            return _LiftTrainFn.apply(x, self, names, *[params[n] for n in names])
+        eng.packed = False
+        pose = eng.forward(x)
+        out = eng.be.empty(tuple(pose.shape), torch.float32)
+        eng.be.copy(out, pose)
+        return out
+
     def _run(self, input, last_stage=-1):
+        if self.training and isinstance(input, torch.Tensor) and input.size(0) > 0:
+            return self._run_train(input)
         if not isinstance(input, torch.Tensor) or not input.is_cuda:
             raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
-        if self.training:
-            raise NotImplementedError("egotap_b200: the training step (BatchNorm batch statistics + backward) is not "
-                                      "built yet; call .eval() (SURVEY.md section 8(f) row f2)")
         if next(self.parameters()).device != input.device:
             raise RuntimeError("egotap_b200: parameters are on %s but input is on %s" % (next(self.parameters()).device, input.device))
         assert input.dim() == 4 and input.size(1) == self.channels_heatmap and input.size(2) == self.W and input.size(3) == self.H, \

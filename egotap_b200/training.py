@@ -606,7 +606,7 @@ class TrainEngine:
                         heads=HEADS, tokens=TOK, out_f32=out, ldo=3 * HID, col_off=col)
 
     # ------------------------------------------------------------------------------------------ optimiser
-    def adamw_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-4, weight_decay=0.0):
+    def adamw_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-4, weight_decay=0.0, grad_scale=1.0):
         """torch.optim.AdamW semantics on every trained parameter, in place (reference model/network.py:72-78,
         options/train_options.py:29-37); re-packs the bf16 operand copies lazily at the next forward."""
         if self.opt_m is None:
@@ -618,16 +618,22 @@ class TrainEngine:
         ks = self.order
         self.be.adamw([self.P[k] for k in ks], [self.grad[k] for k in ks],
                       [self.opt_m[self.offsets[k]:] for k in ks], [self.opt_v[self.offsets[k]:] for k in ks],
-                      self.opt_step, lr, beta1, beta2, eps, weight_decay)
+                      self.opt_step, lr, beta1, beta2, eps, weight_decay, grad_scale)
         self.packed = False
 
-    def train_step(self, x, gt, lr=1e-3, eps=1e-4, weight_decay=0.0, on_stage=None):
+    def train_step(self, x, gt, lr=1e-3, eps=1e-4, weight_decay=0.0, reducer=None):
         """forward + loss + backward + AdamW, all on the current stream; returns the 3-element loss tensor
-        (total, mpjpe term, cos-sim term) without synchronising"""
+        (total, mpjpe term, cos-sim term) without synchronising.  ``reducer`` (ddp.StagedGradAllReduce) sums the
+        gradients over the data-parallel ranks stage by stage while the backward is still running."""
         self.forward(x)
         loss = self.loss_and_grad(gt)
-        self.backward(on_stage=on_stage)
-        self.adamw_step(lr=lr, eps=eps, weight_decay=weight_decay)
+        if reducer is None:
+            self.backward()
+            self.adamw_step(lr=lr, eps=eps, weight_decay=weight_decay)
+        else:
+            self.backward(on_stage=reducer.on_stage)
+            reducer.finish()
+            self.adamw_step(lr=lr, eps=eps, weight_decay=weight_decay, grad_scale=1.0 / reducer.world)
         return loss
 
 

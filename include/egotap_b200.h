@@ -247,9 +247,11 @@ int egotap_b200_embed_grads(const float* dpos_perm, int grid, int n_hm, float* d
 int egotap_b200_pose_loss(const float* pred, const float* gt, long long frames, int joints, const int* parents_host,
                           int n_parents, int drop_first, float lambda_mpjpe, float lambda_cos, float* loss, float* dpose,
                           float* scratch, long long scratch_elems, void* stream);
+/* torch.optim.AdamW on `count` tensors; gradients are multiplied by grad_scale first (1 / world size after a SUM
+ * all-reduce of the data-parallel gradients) */
 int egotap_b200_adamw(float* const* params_host, const float* const* grads_host, float* const* m_host, float* const* v_host,
                       const long long* numel_host, int count, int step, double lr, double beta1, double beta2, double eps,
-                      double weight_decay, void* stream);
+                      double weight_decay, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

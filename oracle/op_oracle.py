@@ -537,12 +537,12 @@ class OracleBackend:
         flat(loss)[:3] = torch.stack([total, mp, cs]).detach().float()
         flat(dpose)[:frames * nj * 3] = dp.float().reshape(-1)
 
-    def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay):
+    def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
         """torch.optim.AdamW (reference model/network.py:72-78); params / grads / m / v: lists of tensors"""
         self.launches += 1
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         for p, g, mm, vv in zip(params, grads, m, v):
-            pf, gf, mf, vf = p.data.view(-1), flat(g)[:p.numel()], flat(mm)[:p.numel()], flat(vv)[:p.numel()]
+            pf, gf, mf, vf = p.data.view(-1), flat(g)[:p.numel()] * grad_scale, flat(mm)[:p.numel()], flat(vv)[:p.numel()]
             pf.mul_(1 - lr * weight_decay)
             mf.mul_(beta1).add_(gf, alpha=1 - beta1)
             vf.mul_(beta2).addcmul_(gf, gf, value=1 - beta2)
