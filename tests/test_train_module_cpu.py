@@ -104,7 +104,9 @@ def _ddp_worker(rank, world, port, q):
         x = synthetic_heatmaps(preset, 1, seed=100 + rank, kind="gauss")
         gt = torch.randn(1, 16, 3, generator=torch.Generator().manual_seed(200 + rank)) * 20
         eng.train_step(x, gt, reducer=red)
-        probe = {k: params[k].clone() for k in ("pose_mlp.pose_fcs.0.weight",
+        # numpy copies: torch tensors travel through multiprocessing queues as shared-memory handles, which die with
+        # the worker
+        probe = {k: params[k].numpy().copy() for k in ("pose_mlp.pose_fcs.0.weight",
                                                 "pos_heatmap_encoder.vit.encoder.layer.0.attention.attention.query.weight",
                                                 "pos_heatmap_encoder.fc1.bn.running_mean")}
         q.put((rank, probe, red.launched, eng.flat_grad.numel()))
@@ -131,7 +133,7 @@ def test_staged_gradient_allreduce_over_gloo():
     launched, total = got[0][2], got[0][3]
     assert launched[0][0] == 0 and launched[-1][1] == total and all(a[1] == b[0] for a, b in zip(launched, launched[1:]))
     assert len(launched) >= 3
-    w0, w1 = got[0][1], got[1][1]
+    w0, w1 = ({k: torch.from_numpy(v) for k, v in g[1].items()} for g in got)
     for k in ("pose_mlp.pose_fcs.0.weight", "pos_heatmap_encoder.vit.encoder.layer.0.attention.attention.query.weight"):
         assert torch.equal(w0[k], w1[k]), k
     assert not torch.equal(w0["pos_heatmap_encoder.fc1.bn.running_mean"], w1["pos_heatmap_encoder.fc1.bn.running_mean"])
