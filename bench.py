@@ -333,6 +333,151 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def time_train_oracle_cpu(preset, steps, batch=4):
+    """The reference's optimisation step (train-mode forward, MPJPE + bone-cosine loss, autograd backward, AdamW) as
+    restated by oracle/train_oracle.py, fp32, all host threads, bounded sample."""
+    import torch
+    import train_oracle as tro
+    import weights
+    from egotap_b200.synthetic import synthetic_heatmaps
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    sd = weights.make_state_dict(preset, seed=0, randomize=False)
+    x = synthetic_heatmaps(preset, batch, seed=1234, kind="gauss")
+    nj = 16 if preset == "UnrealEgo" else 17
+    gt = torch.randn(batch, nj, 3, generator=torch.Generator().manual_seed(7)) * 20
+    _, sd, state, _ = tro.train_step(sd, x, gt, preset)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss, sd, state, _ = tro.train_step(sd, x, gt, preset, opt_state=state)
+    dt = (time.perf_counter() - t0) / steps
+    return dict(fps=batch / dt, ms_per_step=dt * 1e3, cores=torch.get_num_threads(), batch=batch, loss=float(loss))
+
+
+TRAIN_METRIC = "train_frames_per_sec_lifting_net"
+TRAIN_WORKLOAD = "EgoTAP pose-estimator training step (train-mode forward, MPJPE + bone-cosine loss, backward, AdamW), " \
+                 "%s preset, random-init weights, synthetic heatmaps + poses, batch %d per GPU"
+
+
+def run_train_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    r = time_train_oracle_cpu(args.preset, steps=max(1, min(args.steps, 3)))
+    sample = "%d steps x batch %d frames, fp32, %d host threads" % (max(1, min(args.steps, 3)), r["batch"], r["cores"])
+    print(json.dumps(dict(impl="reference", metric=TRAIN_METRIC, value=r["fps"], unit="frames/s", n_gpus=args.gpus,
+                          steps=args.steps, warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True,
+                          scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                          config=dict(workload=TRAIN_WORKLOAD % (args.preset, r["batch"]), preset=args.preset),
+                          cpu_baseline=dict(value=r["fps"], unit="frames/s", cores=r["cores"], kind="port", sample=sample),
+                          e2e=dict(value=r["fps"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                          gpu_launches=0)), flush=True)
+
+
+def run_train(args):
+    """BASELINE config 5: one optimisation step per 'step', per-GPU micro-batch fixed (weak scaling), gradients
+    all-reduced over NCCL in backward-completion order while the backward is still running."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import egotap_b200
+    from egotap_b200 import capi, ddp
+    from egotap_b200.options import make_opt
+    B, K, W = args.batch, args.steps, args.warmup
+    torch.manual_seed(0)
+    net = egotap_b200.EgoTAPAutoEncoder(make_opt(args.preset, b200_precision=args.precision), input_channel_scale=2)
+    net.init_weights("kaiming")
+    net = net.to(dev).train()
+    eng = net.train_engine()
+    red = ddp.StagedGradAllReduce(eng) if world > 1 else None
+    nj = net.num_joints
+    x_host = egotap_b200.synthetic_heatmaps(args.preset, B, seed=1234 + rank, kind="gauss").pin_memory()
+    gt_host = (torch.randn(B, nj, 3, generator=torch.Generator().manual_seed(7 + rank)) * 20).pin_memory()
+    x, gt = x_host.to(dev), gt_host.to(dev)
+    losses = []
+    for _ in range(W):
+        losses.append(eng.train_step(x, gt, reducer=red).clone())
+    torch.cuda.synchronize()
+    launches0 = capi.lib().egotap_b200_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(K):
+            loss = eng.train_step(x, gt, reducer=red)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = capi.lib().egotap_b200_launch_count() - launches0
+    losses.append(loss.clone())
+    # end to end: inputs and targets from pinned host memory every step, the loss read back every step
+    loss_host = torch.empty(4).pin_memory()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        xd, gd = x_host.to(dev, non_blocking=True), gt_host.to(dev, non_blocking=True)
+        loss_host.copy_(eng.train_step(xd, gd, reducer=red), non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    all_recs = capi.profile_kernels(lambda: (eng.forward(x), eng.loss_and_grad(gt), eng.backward(), eng.adamw_step(lr=0.0)))
+    recs = [r for r in all_recs if "flops" in r]
+    gemm_ms, gemm_flops = sum(r["ms"] for r in recs), sum(r["flops"] for r in recs)
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    nsplit = 3 if args.precision != "bf16" else 1
+    by_kernel = {}
+    for r in all_recs:
+        by_kernel[r["name"]] = by_kernel.get(r["name"], 0.0) + r["ms"]
+    total = B * world
+    fps = total * K / (ms * 1e-3)
+    cpu = time_train_oracle_cpu(args.preset, steps=2) if world == 1 else None
+    line = dict(metric=TRAIN_METRIC, value=fps, unit="frames/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16x3 operands, f32 accumulate" if nsplit == 3 else "bf16 operands, f32 accumulate, f32 master weights",
+                data="synthetic",
+                config=dict(workload=TRAIN_WORKLOAD % (args.preset, B), preset=args.preset, batch_per_gpu=B, global_batch=total,
+                            precision=args.precision,
+                            parallelism="dp%d (per-rank micro-batch, staged gradient all-reduce over NCCL)" % world,
+                            l2="activations + gradients >> 126 MB L2 per step, no flush needed"),
+                e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=x_host.numel() * 4 + gt_host.numel() * 4,
+                         d2h_bytes_per_step=16, checked=bool(torch.isfinite(loss_host).all())),
+                gpu_launches=int(launches), clocks=clocks.summary(),
+                roofline=dict(bound="tensor", kernel="gemm_tc_kernel (all %d launches of one training step)" % len(recs),
+                              achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s", frac=achieved / pk["bf16_sustained"],
+                              traffic=None, mma_passes_per_flop=nsplit, gemm_share_of_step=gemm_ms / (ms / K),
+                              peak_source=pk["source"] + ", sustained bf16 figure"),
+                kernel_ms_per_step={k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
+                loss_trace=[float(l[0]) for l in losses],
+                cpu_baseline=(dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
+                                   sample="2 steps x batch %d frames of the same workload, fp32 autograd oracle" % cpu["batch"])
+                              if cpu else None))
+    print(json.dumps(line), flush=True)
+    if args.dump:
+        os.makedirs(os.path.dirname(os.path.abspath(args.dump)), exist_ok=True)
+        with open(args.dump, "w") as f:
+            json.dump(dict(line=line, kernel_launches=all_recs), f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,15 +485,27 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference", "torch_eager"])
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 256 for the lifting workloads, 32 for train)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
-    ap.add_argument("--workload", default="lifting", choices=["lifting", "e2e_rgb"],
-                    help="lifting = BASELINE configs 1-3 (default); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting)")
+    ap.add_argument("--workload", default="lifting", choices=["lifting", "e2e_rgb", "train"],
+                    help="lifting = BASELINE configs 1-3 (default); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting); "
+                         "train = config 5 (optimisation step; reference batch size 32, scripts/train/PoseEstimator/*.sh)")
     ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = 32 if args.workload == "train" else 256
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "train":
+        if args.impl == "reference":
+            run_train_reference(args)
+        elif args.impl == "egotap_b200":
+            if args.gpus > 1 and "RANK" not in os.environ:
+                raise SystemExit("launch N > 1 under torch.distributed.run (see the module docstring)")
+            run_train(args)
+        else:
+            raise SystemExit("--workload train has no torch_eager arm")
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch_eager":
         run_torch_eager(args)

@@ -257,6 +257,10 @@ class EgoTAPAutoEncoder(nn.Module):
         return [sd[lib.egotap_b200_param_name(preset, i).decode()] for i in range(n)]
 
     def _ensure_packed(self):
+        # the engine's own AdamW writes the parameters through raw pointers: tensor version counters do not see it
+        if self._engine is not None and self._engine.opt_step != getattr(self, "_engine_step_seen", 0):
+            self._engine_step_seen = self._engine.opt_step
+            self._packed_versions = None
         tensors = self._param_list()
         versions = tuple((t.data_ptr(), t._version) for t in tensors)
         if versions == self._packed_versions:

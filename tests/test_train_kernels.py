@@ -1,8 +1,11 @@
-"""The SOURCE of the training kernels (egotap_b200/csrc/train_ops.cu, train_model.cu), compiled by g++ against a
-CUDA-on-CPU shim (tests/cuda_emu: CTAs in sequence, threads as fibers with real __syncthreads / warp-shuffle
-semantics) and run here against the op oracle -- op by op on deliberately awkward shapes, and end to end inside the
-training engine.  This checks the kernels' indexing, layouts, reductions and arithmetic without a GPU; the same
-comparisons run on the B200 in tests/test_train_gpu.py."""
+"""Op-level parity of the training kernels (egotap_b200/csrc/train_ops.cu, train_model.cu) with the op oracle, on
+deliberately awkward shapes, through two execution vehicles:
+  * "emu"  (CPU suite): the kernels' own SOURCE compiled by g++ against a CUDA-on-CPU shim (tests/cuda_emu: CTAs in
+    sequence, threads as fibers with real __syncthreads / warp-shuffle semantics) -- checks indexing, layouts,
+    reductions and arithmetic of the kernel code without a GPU
+  * "cuda" (-m gpu): the same comparisons against the real kernels through the C ABI on the B200
+    (tests/gpu_adapter.py mirrors the CPU test arguments on the device)
+and, for "emu", end to end inside the training engine."""
 import os
 import sys
 
@@ -15,15 +18,20 @@ import weights
 from egotap_b200 import training
 from egotap_b200.synthetic import synthetic_heatmaps
 
+sys.path.insert(0, os.path.dirname(__file__))
+
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cuda_emu"))
 import build_emu  # noqa: E402
 
 BF16 = torch.bfloat16
 
 
-@pytest.fixture(scope="module")
-def backends():
-    return build_emu.make_backend()
+@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backends(request):
+    if request.param == "emu":
+        return build_emu.make_backend()
+    from gpu_adapter import GpuOpAdapter
+    return GpuOpAdapter(), op_oracle.OracleBackend()
 
 
 def _pair(rows, cols, poison=True):
@@ -247,6 +255,8 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
     """the whole training step with every training op running on the emulated kernel source (GEMM / attention /
     LayerNorm / ingest / head from the oracle): gradients vs torch.autograd on the restated forward"""
     emu, _ = backends
+    if emu.name != "emu":
+        pytest.skip("engine-level GPU parity lives in tests/test_zz_train_gpu.py")
     preset, batch = "UnrealEgo", 1
     sd = weights.make_state_dict(preset, seed=5)
     params = {k: v.clone().contiguous() for k, v in sd.items()}
