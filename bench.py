@@ -148,6 +148,10 @@ def run_torch_eager(args):
 
 
 def workload_name(args):
+    if getattr(args, "workload", "lifting") == "lifting_gt":
+        return "2-D/3-D keypoints -> ground-truth joint+limb heatmaps synthesised on the GPU (gt_heatmap_kernel) -> EgoTAP " \
+               "lifting net, %s preset, random-init weights, batch %d per GPU (the reference's --use_gt_heatmap path)" \
+               % (args.preset, args.batch)
     if getattr(args, "workload", "lifting") == "e2e_rgb":
         return "stereo RGB 256x256 -> 2 x ResNet-18 U-Net heatmap producers (torch/cuDNN, bf16 autocast) -> EgoTAP " \
                "lifting net (sm_100a kernels), %s preset, random-init weights, batch %d per GPU" % (args.preset, args.batch)
@@ -197,7 +201,22 @@ def run_ours(args):
         rgb_host = [torch.rand(B, 3, 256, 256, generator=g).pin_memory() for _ in range(2)]
         rgb = [t.to(dev) for t in rgb_host]
 
+    kp = None
+    if args.workload == "lifting_gt":
+        # the reference's --use_gt_heatmap path: heatmaps synthesised from keypoints (here on the GPU, per step)
+        import numpy as np
+        from egotap_b200.gt_heatmaps import synthesize
+        n_pts = 16 if args.preset == "UnrealEgo" else 18
+        rng = np.random.default_rng(1234 + rank)
+        kp_host = (torch.from_numpy(rng.uniform(0, 1024, size=(B, 2, n_pts, 2)).astype("float32")).pin_memory(),
+                   torch.from_numpy(rng.normal(0, 30, size=(B, n_pts, 3)).astype("float32")).pin_memory())
+        kp = [t.to(dev) for t in kp_host]
+        x = synthesize(kp[0], kp[1], args.preset)
+        x_host = x.cpu()
+
     def local_step():          # this rank's shard only: no collective (safe to call on a single rank)
+        if kp is not None:
+            return net.predict_pose(synthesize(kp[0], kp[1], args.preset, out=x))
         return est(rgb[0], rgb[1]) if est is not None else net.predict_pose(x)
 
     def step():                # what is timed: the shard + the final pose gather (the path's only collective)
@@ -230,7 +249,17 @@ def run_ours(args):
     launches = capi.lib().egotap_b200_launch_count() - launches0
     # ---------------- end to end: pinned host buffers in, pinned host poses out, copies inside the timed region
     host_out = [torch.empty((B, net.num_joints, 3)).pin_memory() for _ in range(K)]
-    if est is None:
+    if kp is not None:
+        h2d, d2h = kp_host[0].numel() * 4 + kp_host[1].numel() * 4, B * net.num_joints * 3 * 4
+
+        def run_e2e():
+            for i in range(K):
+                a = kp_host[0].to(dev, non_blocking=True)
+                b = kp_host[1].to(dev, non_blocking=True)
+                host_out[i].copy_(net.predict_pose(synthesize(a, b, args.preset, out=x)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        run_e2e()
+    elif est is None:
         pipe = HostPipeline(net, B)
         host_in = [x_host, x_host.clone().pin_memory()]
         pipe.run([host_in[i % 2] for i in range(min(W, 2))], host_out)
@@ -295,7 +324,8 @@ def run_ours(args):
     nb = 2 * (2 if nsplit == 3 else 1)                       # bytes per operand element written (bf16 hi [+ lo])
     rows_ln = B * 576
     hbm_bytes = {"layernorm1024_kernel": rows_ln * 1024 * (4 + nb),
-                 "ingest_kernel": B * 6 * J * 4096 * (4 + nb)}
+                 "ingest_kernel": B * 6 * J * 4096 * (4 + nb),
+                 "gt_heatmap_kernel": B * 6 * J * 4096 * 4}              # the heatmap stack written once; inputs are ~0.5 KB/frame
     hbm = {}
     for name, nbytes in hbm_bytes.items():
         ts = [r["ms"] for r in all_recs if r["name"] == name]
@@ -487,8 +517,9 @@ def main():
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 256 for the lifting workloads, 32 for train)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
-    ap.add_argument("--workload", default="lifting", choices=["lifting", "e2e_rgb", "train"],
-                    help="lifting = BASELINE configs 1-3 (default); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting); "
+    ap.add_argument("--workload", default="lifting", choices=["lifting", "lifting_gt", "e2e_rgb", "train"],
+                    help="lifting = BASELINE configs 1-3 (default); lifting_gt = the same with the input heatmaps synthesised on "
+                         "the GPU from keypoints each step (--use_gt_heatmap path); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting); "
                          "train = config 5 (optimisation step; reference batch size 32, scripts/train/PoseEstimator/*.sh)")
     ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
     args = ap.parse_args()

@@ -29,7 +29,7 @@ EXPORTS = [
     "egotap_b200_layernorm_bwd", "egotap_b200_softmax_bwd", "egotap_b200_bn_stats", "egotap_b200_bn_apply",
     "egotap_b200_bn_bwd", "egotap_b200_regroup_gather", "egotap_b200_pu_cell_fwd", "egotap_b200_pu_cell_bwd",
     "egotap_b200_pu_bridge_gate_bwd", "egotap_b200_head_bwd", "egotap_b200_embed_grads", "egotap_b200_pose_loss",
-    "egotap_b200_adamw",
+    "egotap_b200_adamw", "egotap_b200_gt_heatmaps",
 ]
 
 
@@ -85,6 +85,7 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_head_bwd": [P, P, LL, P, P, P, LL, I, P, LL, P, P, P, P, P, P, LL, P],
         "egotap_b200_embed_grads": [P, I, I, P, P, P],
         "egotap_b200_pose_loss": [P, P, LL, I, C.POINTER(C.c_int), I, I, F, F, P, P, P, LL, P],
+        "egotap_b200_gt_heatmaps": [P, P, LL, I, P, P],
         "egotap_b200_adamw": [C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(LL), I, I] + [C.c_double] * 6 + [P],
     }
 
@@ -425,6 +426,10 @@ class CudaBackend:
         check(self.L.egotap_b200_pose_loss(_ptr(pred), _ptr(gt), frames, nj, arr, len(parents), int(drop_first), lambda_mpjpe,
                                            lambda_cos, _ptr(loss), _ptr(dpose), _ptr(scratch), scratch.numel(), self._st()),
               "pose_loss")
+
+    def gt_heatmaps(self, pts2d, pts3d_left, frames, preset, out):
+        check(self.L.egotap_b200_gt_heatmaps(_ptr(pts2d), _ptr(pts3d_left), frames, PRESET_ID[preset], _ptr(out), self._st()),
+              "gt_heatmaps")
 
     def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
         n = len(params)

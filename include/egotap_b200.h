@@ -253,6 +253,14 @@ int egotap_b200_adamw(float* const* params_host, const float* const* grads_host,
                       const long long* numel_host, int count, int step, double lr, double beta1, double beta2, double eps,
                       double weight_decay, double grad_scale, void* stream);
 
+/* Ground-truth heatmap synthesis: keypoints -> the lifting input (frames, 6J, 64, 64) =
+ * [joint L | joint R | cos L | sin L | cos R | sin R], as the reference builds it on the CPU under --use_gt_heatmap
+ * (utils/projection.py:263-279, utils/data.py:175-252, dataloader/data_loader.py:127-132,193-199,
+ * model/egotap_autoencoder_model.py:176-213).  pts2d: (frames, 2 views, J+1, 2) in 1024-pixel image coordinates;
+ * pts3d_left: (frames, J+1, 3) = local pose + left pelvis (the limb elevation angle of BOTH views comes from it). */
+int egotap_b200_gt_heatmaps(const float* pts2d, const float* pts3d_left, long long frames, int preset, float* out,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -537,6 +537,16 @@ class OracleBackend:
         flat(loss)[:3] = torch.stack([total, mp, cs]).detach().float()
         flat(dpose)[:frames * nj * 3] = dp.float().reshape(-1)
 
+    def gt_heatmaps(self, pts2d, pts3d_left, frames, preset, out):
+        """keypoints -> (frames, 6J, 64, 64) lifting input; semantics in oracle/gt_heatmap_oracle.py"""
+        import gt_heatmap_oracle as gto
+        self.launches += 1
+        p2, p3 = pts2d.numpy(), pts3d_left.numpy()
+        for b in range(frames):
+            # the right view's own 3-D points only matter for theta, which the reference takes from the left view
+            hm = gto.lifting_input(p2[b, 0], p2[b, 1], p3[b], p3[b], preset)
+            out[b].copy_(torch.from_numpy(hm))
+
     def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
         """torch.optim.AdamW (reference model/network.py:72-78); params / grads / m / v: lists of tensors"""
         self.launches += 1

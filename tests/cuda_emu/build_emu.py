@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "egotap_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
-SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "train_ops.cu"), os.path.join(CSRC, "train_model.cu")]
+SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "train_ops.cu"), os.path.join(CSRC, "train_model.cu"),
+           os.path.join(CSRC, "gt_heatmap.cu")]
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 
 
