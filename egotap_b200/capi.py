@@ -226,6 +226,14 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
          b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
     """Op-level entry used by the tests: D = epi(A @ B^T).  ``epi`` keys mirror ``egotap_epilogue``;
     tensor-valued keys take CUDA tensors."""
+    d = gemm_desc(a_hi, a_lo, b_hi, b_lo, M, N, K, groups=groups, a_group=a_group, b_group=b_group, a_rows=a_rows,
+                  b_rows=b_rows, lda=lda, ldb=ldb, precision=precision, variant=variant, **epi)
+    check(lib().egotap_b200_gemm(C.byref(d), current_stream()), "gemm")
+
+
+def gemm_desc(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0), a_rows=None,
+              b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
+    """the ``egotap_gemm`` descriptor for D = epi(A @ B^T) (no launch)"""
     d = Gemm()
     d.a = Operand(_ptr(a_hi), _ptr(a_lo), lda or K, a_rows or M, *a_group)
     d.b = Operand(_ptr(b_hi), _ptr(b_lo), ldb or K, b_rows or N, *b_group)
@@ -243,7 +251,7 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
         raise TypeError("unknown epilogue fields: %s" % sorted(epi))
     if e.ldo == 0:
         e.ldo = N
-    check(lib().egotap_b200_gemm(C.byref(d), current_stream()), "gemm")
+    return d
 
 
 def profile_kernels(fn):
@@ -298,142 +306,180 @@ class CudaBackend:
     def _st():
         return current_stream()
 
+    # ---- one choke point for every library call, so a whole training step can be recorded once and replayed without
+    # re-running the Python marshalling (the step issues ~700 launches; see TrainEngine.train_step)
+    _tape = None
+
+    def _fn(self, name):
+        return getattr(self.L, name)
+
+    def _raise(self, name, rc):
+        check(rc, name)
+
+    def _c(self, name, *args):
+        fn = self._fn(name)
+        rc = fn(*args)
+        if rc:
+            self._raise(name, rc)
+        if self._tape is not None:
+            self._tape.append((fn, args, name))
+
+    def callback(self, fn, *args):
+        """a host-side callback inside a step (e.g. launching the all-reduce of a finished gradient slice)"""
+        fn(*args)
+        if self._tape is not None:
+            self._tape.append((fn, args, None))
+
+    def begin_record(self):
+        self._tape = []
+        self._tape_stream = self._st()
+
+    def end_record(self):
+        tape, self._tape = self._tape, None
+        return (tape, self._tape_stream)
+
+    def can_replay(self, recorded):
+        return recorded is not None and recorded[1] == self._st()
+
+    def replay(self, recorded):
+        for fn, args, name in recorded[0]:
+            rc = fn(*args)
+            if name is not None and rc:
+                self._raise(name, rc)
+
     # ---- memory
     def empty(self, shape, dtype=None):
         import torch
         return torch.empty(shape, dtype=dtype or torch.float32, device=self.device)
 
     def zero(self, t):
-        check(self.L.egotap_b200_zero(t.data_ptr(), t.numel() * t.element_size(), self._st()), "zero")
+        self._c("egotap_b200_zero", t.data_ptr(), t.numel() * t.element_size(), self._st())
 
     def copy(self, dst, src):
         assert dst.numel() == src.numel() and dst.element_size() == src.element_size()
-        check(self.L.egotap_b200_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), self._st()), "copy")
+        self._c("egotap_b200_copy", dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), self._st())
 
     def add3(self, a, b, c, out, n):
-        check(self.L.egotap_b200_add3(_ptr(a), _ptr(b), _ptr(c), _ptr(out), n, self._st()), "add3")
+        self._c("egotap_b200_add3", _ptr(a), _ptr(b), _ptr(c), _ptr(out), n, self._st())
 
     # ---- round-1 ops
     def gemm(self, *a, **k):
-        gemm(*a, **k)
+        d = gemm_desc(*a, **k)
+        self._c("egotap_b200_gemm", C.byref(d), self._st())
 
     def split2d(self, src, rows, cols, src_ld, hi, lo, dst_ld):
-        check(self.L.egotap_b200_split2d(_ptr(src), rows, cols, src_ld, _ptr(hi), _ptr(lo), dst_ld, self._st()), "split2d")
+        self._c("egotap_b200_split2d", _ptr(src), rows, cols, src_ld, _ptr(hi), _ptr(lo), dst_ld, self._st())
 
     def ingest(self, x, J, p_hi, p_lo, l_hi, l_lo):
-        check(self.L.egotap_b200_ingest(x.data_ptr(), x.shape[0], self._preset_of_J[J], _ptr(p_hi), _ptr(p_lo), _ptr(l_hi),
-                                        _ptr(l_lo), self._st()), "ingest")
+        self._c("egotap_b200_ingest", x.data_ptr(), x.shape[0], self._preset_of_J[J], _ptr(p_hi), _ptr(p_lo), _ptr(l_hi),
+                                        _ptr(l_lo), self._st())
 
     def fill_dummy(self, hidden, dummy, B, tokens, live):
         if tokens > live:
-            check(self.L.egotap_b200_fill_dummy(_ptr(hidden), _ptr(dummy), B, tokens, live, self._st()), "fill_dummy")
+            self._c("egotap_b200_fill_dummy", _ptr(hidden), _ptr(dummy), B, tokens, live, self._st())
 
     def pos_permute(self, pos, mask_token, grid, n_hm, pos_perm, dummy):
-        check(self.L.egotap_b200_pos_permute(_ptr(pos), _ptr(mask_token), grid, n_hm, _ptr(pos_perm), _ptr(dummy),
-                                             self._st()), "pos_permute")
+        self._c("egotap_b200_pos_permute", _ptr(pos), _ptr(mask_token), grid, n_hm, _ptr(pos_perm), _ptr(dummy),
+                                             self._st())
 
     def layernorm(self, x, w, b, frames, rows_in, rows_out, eps, out_hi, out_lo, out_f32):
-        check(self.L.egotap_b200_layernorm(_ptr(x), _ptr(w), _ptr(b), frames, rows_in, rows_out, eps, _ptr(out_hi),
-                                           _ptr(out_lo), _ptr(out_f32), self._st()), "layernorm")
+        self._c("egotap_b200_layernorm", _ptr(x), _ptr(w), _ptr(b), frames, rows_in, rows_out, eps, _ptr(out_hi),
+                                           _ptr(out_lo), _ptr(out_f32), self._st())
 
     def attention(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, frames, precision):
-        check(self.L.egotap_b200_attention(_ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
-                                           frames, precision, self._st()), "attention")
+        self._c("egotap_b200_attention", _ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
+                                           frames, precision, self._st())
 
     def pu_bridge_gate(self, f, f_ld, f_col, e, e_ld, X, rows, hi, lo):
-        check(self.L.egotap_b200_pu_bridge_gate(_ptr(f), f_ld, f_col, _ptr(e), e_ld, X, rows, _ptr(hi), _ptr(lo), self._st()),
-              "pu_bridge_gate")
+        self._c("egotap_b200_pu_bridge_gate", _ptr(f), f_ld, f_col, _ptr(e), e_ld, X, rows, _ptr(hi), _ptr(lo), self._st())
 
     def head(self, e, e_ld, skel, Wp, bp, Wg, bg, frames, J, pose):
-        check(self.L.egotap_b200_head(_ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(bp), _ptr(Wg), _ptr(bg), frames, J, _ptr(pose),
-                                      self._st()), "head")
+        self._c("egotap_b200_head", _ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(bp), _ptr(Wg), _ptr(bg), frames, J, _ptr(pose),
+                                      self._st())
 
     # ---- training ops
     def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows):
-        check(self.L.egotap_b200_transpose_split(_ptr(src), rows, cols, src_ld, rows_in, rows_out, _ptr(rm_hi), _ptr(rm_lo),
-                                                 rm_ld, _ptr(t_hi), _ptr(t_lo), t_ld, pad_rows, self._st()), "transpose_split")
+        self._c("egotap_b200_transpose_split", _ptr(src), rows, cols, src_ld, rows_in, rows_out, _ptr(rm_hi), _ptr(rm_lo),
+                                                 rm_ld, _ptr(t_hi), _ptr(t_lo), t_ld, pad_rows, self._st())
 
     def transpose_bf16(self, s_hi, s_lo, rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, d_hi, d_lo, d_ld, d_g0s, d_g1s, pad_rows):
-        check(self.L.egotap_b200_transpose_bf16(_ptr(s_hi), _ptr(s_lo), rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, _ptr(d_hi),
-                                                _ptr(d_lo), d_ld, d_g0s, d_g1s, pad_rows, self._st()), "transpose_bf16")
+        self._c("egotap_b200_transpose_bf16", _ptr(s_hi), _ptr(s_lo), rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, _ptr(d_hi),
+                                                _ptr(d_lo), d_ld, d_g0s, d_g1s, pad_rows, self._st())
 
     def colsum(self, src, rows, cols, ld, rows_in, rows_out, out, scratch):
-        check(self.L.egotap_b200_colsum(_ptr(src), rows, cols, ld, rows_in, rows_out, _ptr(out), _ptr(scratch),
-                                        scratch.numel(), self._st()), "colsum")
+        self._c("egotap_b200_colsum", _ptr(src), rows, cols, ld, rows_in, rows_out, _ptr(out), _ptr(scratch),
+                                        scratch.numel(), self._st())
 
     def reduce_partials(self, partials, G, n, out):
-        check(self.L.egotap_b200_reduce_partials(_ptr(partials), G, n, _ptr(out), self._st()), "reduce_partials")
+        self._c("egotap_b200_reduce_partials", _ptr(partials), G, n, _ptr(out), self._st())
 
     def gelu_fwd(self, u, n, out_hi, out_lo):
-        check(self.L.egotap_b200_gelu_fwd(_ptr(u), n, _ptr(out_hi), _ptr(out_lo), self._st()), "gelu_fwd")
+        self._c("egotap_b200_gelu_fwd", _ptr(u), n, _ptr(out_hi), _ptr(out_lo), self._st())
 
     def gelu_bwd(self, dg, u, n):
-        check(self.L.egotap_b200_gelu_bwd(_ptr(dg), _ptr(u), n, self._st()), "gelu_bwd")
+        self._c("egotap_b200_gelu_bwd", _ptr(dg), _ptr(u), n, self._st())
 
     def layernorm_bwd(self, dy, x, w, frames, rows_in, rows_out, eps, dx, accumulate, dw, db, scratch):
-        check(self.L.egotap_b200_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(w), frames, rows_in, rows_out, eps, _ptr(dx),
+        self._c("egotap_b200_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(w), frames, rows_in, rows_out, eps, _ptr(dx),
                                                int(accumulate), _ptr(dw), _ptr(db), _ptr(scratch), scratch.numel(),
-                                               self._st()), "layernorm_bwd")
+                                               self._st())
 
     def softmax_bwd(self, S, dP, rows, cols, scale, p_hi, p_lo, ds_hi, ds_lo):
-        check(self.L.egotap_b200_softmax_bwd(_ptr(S), _ptr(dP), rows, cols, scale, _ptr(p_hi), _ptr(p_lo), _ptr(ds_hi),
-                                             _ptr(ds_lo), self._st()), "softmax_bwd")
+        self._c("egotap_b200_softmax_bwd", _ptr(S), _ptr(dP), rows, cols, scale, _ptr(p_hi), _ptr(p_lo), _ptr(ds_hi),
+                                             _ptr(ds_lo), self._st())
 
     def bn_stats(self, y, rows, cols, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, mean, rstd,
                  scale, shift, scratch):
-        check(self.L.egotap_b200_bn_stats(_ptr(y), rows, cols, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+        self._c("egotap_b200_bn_stats", _ptr(y), rows, cols, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
                                           _ptr(num_batches_tracked), momentum, eps, _ptr(mean), _ptr(rstd), _ptr(scale),
-                                          _ptr(shift), _ptr(scratch), scratch.numel(), self._st()), "bn_stats")
+                                          _ptr(shift), _ptr(scratch), scratch.numel(), self._st())
 
     def bn_apply(self, y, rows, cols, scale, shift, out_hi, out_lo, out_ld, out_f32, f32_ld, J, col_off):
-        check(self.L.egotap_b200_bn_apply(_ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(out_hi), _ptr(out_lo), out_ld,
-                                          _ptr(out_f32), f32_ld, J, col_off, self._st()), "bn_apply")
+        self._c("egotap_b200_bn_apply", _ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(out_hi), _ptr(out_lo), out_ld,
+                                          _ptr(out_f32), f32_ld, J, col_off, self._st())
 
     def bn_bwd(self, da, y, rows, cols, scale, shift, mean, rstd, dgamma, dbeta, scratch):
-        check(self.L.egotap_b200_bn_bwd(_ptr(da), _ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
-                                        _ptr(dgamma), _ptr(dbeta), _ptr(scratch), scratch.numel(), self._st()), "bn_bwd")
+        self._c("egotap_b200_bn_bwd", _ptr(da), _ptr(y), rows, cols, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                        _ptr(dgamma), _ptr(dbeta), _ptr(scratch), scratch.numel(), self._st())
 
     def regroup_gather(self, dE, e_ld, col_off, frames, J, cols, out):
-        check(self.L.egotap_b200_regroup_gather(_ptr(dE), e_ld, col_off, frames, J, cols, _ptr(out), self._st()),
-              "regroup_gather")
+        self._c("egotap_b200_regroup_gather", _ptr(dE), e_ld, col_off, frames, J, cols, _ptr(out), self._st())
 
     def pu_cell_fwd(self, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, h_hi, h_lo, hg_hi, hg_lo, t, J, B):
-        check(self.L.egotap_b200_pu_cell_fwd(_ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(h_hi),
-                                             _ptr(h_lo), _ptr(hg_hi), _ptr(hg_lo), t, J, B, self._st()), "pu_cell_fwd")
+        self._c("egotap_b200_pu_cell_fwd", _ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(h_hi),
+                                             _ptr(h_lo), _ptr(hg_hi), _ptr(hg_lo), t, J, B, self._st())
 
     def pu_cell_bwd(self, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, dOut, dhg, dc, dG, dg_rs, dg_ts, dF, df_rs, df_ts, dgp_hi,
                     dgp_lo, t, J, B):
-        check(self.L.egotap_b200_pu_cell_bwd(_ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(dOut),
+        self._c("egotap_b200_pu_cell_bwd", _ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(dOut),
                                              _ptr(dhg), _ptr(dc), _ptr(dG), dg_rs, dg_ts, _ptr(dF), df_rs, df_ts, _ptr(dgp_hi),
-                                             _ptr(dgp_lo), t, J, B, self._st()), "pu_cell_bwd")
+                                             _ptr(dgp_lo), t, J, B, self._st())
 
     def pu_bridge_gate_bwd(self, dE, e_ld, F0, f_ld, f_col, E, X, rows, dF, df_ld):
-        check(self.L.egotap_b200_pu_bridge_gate_bwd(_ptr(dE), e_ld, _ptr(F0), f_ld, f_col, _ptr(E), X, rows, _ptr(dF), df_ld,
-                                                    self._st()), "pu_bridge_gate_bwd")
+        self._c("egotap_b200_pu_bridge_gate_bwd", _ptr(dE), e_ld, _ptr(F0), f_ld, f_col, _ptr(E), X, rows, _ptr(dF), df_ld,
+                                                    self._st())
 
     def head_bwd(self, dpose, e, e_ld, skel, Wp, Wg, frames, J, dE, de_ld, dSkel, dWp, dbp, dWg, dbg, scratch):
-        check(self.L.egotap_b200_head_bwd(_ptr(dpose), _ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(Wg), frames, J, _ptr(dE), de_ld,
+        self._c("egotap_b200_head_bwd", _ptr(dpose), _ptr(e), e_ld, _ptr(skel), _ptr(Wp), _ptr(Wg), frames, J, _ptr(dE), de_ld,
                                           _ptr(dSkel), _ptr(dWp), _ptr(dbp), _ptr(dWg), _ptr(dbg), _ptr(scratch),
-                                          scratch.numel(), self._st()), "head_bwd")
+                                          scratch.numel(), self._st())
 
     def embed_grads(self, dpos_perm, grid, n_hm, dpos, dmask):
-        check(self.L.egotap_b200_embed_grads(_ptr(dpos_perm), grid, n_hm, _ptr(dpos), _ptr(dmask), self._st()), "embed_grads")
+        self._c("egotap_b200_embed_grads", _ptr(dpos_perm), grid, n_hm, _ptr(dpos), _ptr(dmask), self._st())
 
     def pose_loss(self, pred, gt, frames, nj, parents, drop_first, lambda_mpjpe, lambda_cos, loss, dpose, scratch=None):
         arr = (C.c_int * len(parents))(*parents)
         if scratch is None:
             scratch = self.empty((2 * frames + 64,))
-        check(self.L.egotap_b200_pose_loss(_ptr(pred), _ptr(gt), frames, nj, arr, len(parents), int(drop_first), lambda_mpjpe,
-                                           lambda_cos, _ptr(loss), _ptr(dpose), _ptr(scratch), scratch.numel(), self._st()),
-              "pose_loss")
+        self._c("egotap_b200_pose_loss", _ptr(pred), _ptr(gt), frames, nj, arr, len(parents), int(drop_first), lambda_mpjpe,
+                                           lambda_cos, _ptr(loss), _ptr(dpose), _ptr(scratch), scratch.numel(), self._st())
 
     def gt_heatmaps(self, pts2d, pts3d_left, frames, preset, out):
-        check(self.L.egotap_b200_gt_heatmaps(_ptr(pts2d), _ptr(pts3d_left), frames, PRESET_ID[preset], _ptr(out), self._st()),
-              "gt_heatmaps")
+        self._c("egotap_b200_gt_heatmaps", _ptr(pts2d), _ptr(pts3d_left), frames, PRESET_ID[preset], _ptr(out), self._st())
 
     def adamw(self, params, grads, m, v, step, lr, beta1, beta2, eps, weight_decay, grad_scale=1.0):
         n = len(params)
         mk = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
         numel = (C.c_longlong * n)(*[p.numel() for p in params])
-        check(self.L.egotap_b200_adamw(mk(params), mk(grads), mk(m), mk(v), numel, n, step, lr, beta1, beta2, eps, weight_decay,
-                                       grad_scale, self._st()), "adamw")
+        self._c("egotap_b200_adamw", mk(params), mk(grads), mk(m), mk(v), numel, n, step, lr, beta1, beta2, eps, weight_decay,
+                                       grad_scale, self._st())

@@ -146,6 +146,12 @@ class TrainEngine:
         self.opt_m = self.opt_v = None
         self.opt_step = 0
         self.batch = 0
+        # Replay of a recorded step: the ~700 library calls of forward + loss + backward are recorded once per batch size
+        # (backend.begin_record) and re-issued from the record afterwards, skipping this file's Python entirely -- at
+        # the reference's batch size (32) the host would otherwise be the bottleneck.  Needs stable device pointers:
+        # train_step copies its inputs into engine-owned buffers.
+        self.use_tape = hasattr(self.be, "begin_record")
+        self._tape, self._tape_key = None, None
         self._alloc_weights()
         self.scr = self.be.empty((4 * 1024 * 1024,), torch.float32)     # reduction scratch shared by the small ops
         self.partials = None
@@ -317,7 +323,9 @@ class TrainEngine:
         S["dhg"], S["dc"], S["dgp"] = f32(B, PUH), f32(B, PUH), pair(B, 4 * PUH)
         S["dpos"] = f32(TOK, HID)
         S["dpose"] = f32(B, self.nj, 3)
+        self.x_in, self.gt_in = f32(B, 6 * J, 64, 64), f32(B, self.nj, 3)
         self.batch = B
+        self._tape = None
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, x):
@@ -430,7 +438,11 @@ class TrainEngine:
 
         def done():
             if on_stage is not None:
-                on_stage(stage[0], *self.stages[stage[0]])
+                cb = getattr(be, "callback", None)       # recorded on the tape when a step is being recorded
+                if cb is not None:
+                    cb(on_stage, stage[0], *self.stages[stage[0]])
+                else:
+                    on_stage(stage[0], *self.stages[stage[0]])
             stage[0] += 1
         # ---- head
         gh = self.global_head
@@ -625,13 +637,33 @@ class TrainEngine:
         """forward + loss + backward + AdamW, all on the current stream; returns the 3-element loss tensor
         (total, mpjpe term, cos-sim term) without synchronising.  ``reducer`` (ddp.StagedGradAllReduce) sums the
         gradients over the data-parallel ranks stage by stage while the backward is still running."""
-        self.forward(x)
-        loss = self.loss_and_grad(gt)
+        on_stage = None if reducer is None else reducer.on_stage
+        if not self.use_tape:
+            self.forward(x)
+            loss = self.loss_and_grad(gt)
+            self.backward(on_stage=on_stage)
+        else:
+            be = self.be
+            self._alloc(x.shape[0])
+            be.copy(self.x_in, x)
+            be.copy(self.gt_in, gt)
+            key = (x.shape[0], id(reducer))
+            if self._tape is not None and self._tape_key == key and be.can_replay(self._tape):
+                be.replay(self._tape)
+                loss = self.loss
+            else:
+                self.packed = False                       # the recorded step must contain the re-pack of the weights
+                be.begin_record()
+                try:
+                    self.forward(self.x_in)
+                    loss = self.loss_and_grad(self.gt_in)
+                    self.backward(on_stage=on_stage)
+                finally:
+                    tape = be.end_record()
+                self._tape, self._tape_key = tape, key
         if reducer is None:
-            self.backward()
             self.adamw_step(lr=lr, eps=eps, weight_decay=weight_decay)
         else:
-            self.backward(on_stage=reducer.on_stage)
             reducer.finish()
             self.adamw_step(lr=lr, eps=eps, weight_decay=weight_decay, grad_scale=1.0 / reducer.world)
         return loss

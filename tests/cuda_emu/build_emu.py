@@ -54,7 +54,7 @@ def make_backend():
         name = "emu"
 
         def __init__(self):                      # no CUDA device, no product library
-            self.L = _Checked(lib, check)
+            self.L = lib
             self.device = torch.device("cpu")
             self._preset_of_J = {15: 0, 17: 1}
 
@@ -62,40 +62,30 @@ def make_backend():
         def _st():
             return None
 
+        def _raise(self, name, rc):
+            check(rc, name)
+
         def empty(self, shape, dtype=None):
             return orc.empty(shape, dtype or torch.float32)
 
+        def _py(self, fn, *a, **k):              # an oracle-served op, recorded on the tape like a library call
+            fn(*a, **k)
+            if self._tape is not None:
+                self._tape.append((lambda: fn(*a, **k), (), None))
+
         # round-1 ops: oracle
-        gemm = staticmethod(orc.gemm)
-        split2d = staticmethod(orc.split2d)
-        ingest = staticmethod(orc.ingest)
-        fill_dummy = staticmethod(orc.fill_dummy)
-        pos_permute = staticmethod(orc.pos_permute)
-        layernorm = staticmethod(orc.layernorm)
-        attention = staticmethod(orc.attention)
-        pu_bridge_gate = staticmethod(orc.pu_bridge_gate)
-        head = staticmethod(orc.head)
-        add3 = staticmethod(orc.add3)
+        def gemm(self, *a, **k): self._py(orc.gemm, *a, **k)
+        def split2d(self, *a): self._py(orc.split2d, *a)
+        def ingest(self, *a): self._py(orc.ingest, *a)
+        def fill_dummy(self, *a): self._py(orc.fill_dummy, *a)
+        def pos_permute(self, *a): self._py(orc.pos_permute, *a)
+        def layernorm(self, *a): self._py(orc.layernorm, *a)
+        def attention(self, *a): self._py(orc.attention, *a)
+        def pu_bridge_gate(self, *a): self._py(orc.pu_bridge_gate, *a)
+        def head(self, *a): self._py(orc.head, *a)
+        def add3(self, *a): self._py(orc.add3, *a)
 
     return EmuBackend(), orc
-
-
-class _Checked:
-    """wraps the emulation library so that the product's check(rc, what) helper (which reads the PRODUCT library's error
-    string) is bypassed: a non-zero return raises here with the emulation library's own message"""
-
-    def __init__(self, lib, check):
-        self._lib, self._check = lib, check
-
-    def __getattr__(self, name):
-        fn = getattr(self._lib, name)
-        if name in ("egotap_b200_launch_count", "egotap_b200_last_error"):
-            return fn
-
-        def call(*a):
-            self._check(fn(*a), name)
-            return 0
-        return call
 
 
 if __name__ == "__main__":

@@ -280,3 +280,30 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
     for k in ("pose_mlp.pose_fcs.0.weight", "pos_heatmap_encoder.vit.encoder.layer.1.output.dense.weight"):
         upd_ref, upd = ref_sd[k] - sd[k], params[k] - sd[k]
         assert (upd - upd_ref).abs().max().item() <= 5e-2 * upd_ref.abs().max().item() + 2e-7, k
+
+
+def test_recorded_step_replays_identically(backends):
+    """TrainEngine records the library calls of one step and replays them afterwards (no Python orchestration on the
+    hot path): two steps (record, replay) must leave exactly the same weights as two steps without"""
+    emu, _ = backends
+    if emu.name != "emu":
+        pytest.skip("host-side logic; the CUDA engine uses the same code path in tests/test_zz_train_gpu.py")
+    preset, batch = "EgoCap", 1
+    sd = weights.make_state_dict(preset, seed=5)
+    x = synthetic_heatmaps(preset, batch, seed=17, kind="gauss")
+    gt = torch.randn(batch, 17, 3, generator=torch.Generator().manual_seed(19)) * 20
+    results = []
+    for use_tape in (True, False):
+        params = {k: v.clone().contiguous() for k, v in sd.items()}
+        eng = training.TrainEngine(preset, params, precision="bf16", backend=emu)
+        assert eng.use_tape
+        eng.use_tape = use_tape
+        losses = [float(eng.train_step(x.clone(), gt.clone())[0]) for _ in range(2)]
+        if use_tape:
+            assert eng._tape is not None and len(eng._tape[0]) > 300
+        results.append((losses, {k: params[k].clone() for k in ("pose_mlp.pose_fcs.0.weight",
+                                                                "pos_heatmap_encoder.vit.encoder.layer.0.output.dense.weight",
+                                                                "rot_heatmap_encoder.fc1.bn.running_var")}))
+    assert results[0][0] == results[1][0] and results[0][0][0] != results[0][0][1]
+    for k in results[0][1]:
+        assert torch.equal(results[0][1][k], results[1][1][k]), k
