@@ -152,6 +152,10 @@ class TrainEngine:
         # train_step copies its inputs into engine-owned buffers.
         self.use_tape = hasattr(self.be, "begin_record")
         self._tape, self._tape_key = None, None
+        # Opt-in: the same step captured in a CUDA graph (single-GPU; the staged all-reduce stays on the replay path).
+        # Step 1 runs eagerly (allocations, per-device kernel attributes), step 2 is captured, later steps replay.
+        self.use_cuda_graph = False
+        self._graph, self._graph_key, self._graph_warm = None, None, None
         self._alloc_weights()
         self.scr = self.be.empty((4 * 1024 * 1024,), torch.float32)     # reduction scratch shared by the small ops
         self.partials = None
@@ -633,12 +637,41 @@ class TrainEngine:
                       self.opt_step, lr, beta1, beta2, eps, weight_decay, grad_scale)
         self.packed = False
 
+    def _graph_step(self, x, gt):
+        """forward + loss + backward through a CUDA graph (torch.cuda.CUDAGraph owns capture and replay; every launch
+        inside is ours, enqueued on the capturing stream through the C ABI)"""
+        B = x.shape[0]
+        self._alloc(B)
+        self.be.copy(self.x_in, x)
+        self.be.copy(self.gt_in, gt)
+
+        def body():
+            self.packed = False
+            self.forward(self.x_in)
+            self.loss_and_grad(self.gt_in)
+            self.backward()
+        if self._graph is not None and self._graph_key == B:
+            self._graph.replay()
+        elif self._graph_warm != B:
+            body()                                  # eager: also performs every lazy allocation
+            self._graph_warm, self._graph = B, None
+        else:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graph, self._graph_key = g, B
+            g.replay()
+
     def train_step(self, x, gt, lr=1e-3, eps=1e-4, weight_decay=0.0, reducer=None):
         """forward + loss + backward + AdamW, all on the current stream; returns the 3-element loss tensor
         (total, mpjpe term, cos-sim term) without synchronising.  ``reducer`` (ddp.StagedGradAllReduce) sums the
         gradients over the data-parallel ranks stage by stage while the backward is still running."""
         on_stage = None if reducer is None else reducer.on_stage
-        if not self.use_tape:
+        if self.use_cuda_graph and reducer is None:
+            self._graph_step(x, gt)
+            loss = self.loss
+        elif not self.use_tape:
             self.forward(x)
             loss = self.loss_and_grad(gt)
             self.backward(on_stage=on_stage)

@@ -159,3 +159,20 @@ def test_reference_style_loop_on_the_cuda_module():
     with torch.no_grad():
         p_eval = net.predict_pose(x.cuda())
     assert torch.isfinite(p_eval).all()
+
+
+def test_cuda_graph_step_equals_replayed_step():
+    """opt-in CUDA-graph issue of forward + loss + backward: step 1 eager, step 2 captured, step 3 replayed"""
+    preset = "UnrealEgo"
+    outs = []
+    for graph in (False, True):
+        sd, params, eng = _engine(preset, "bf16")
+        eng.use_cuda_graph = graph
+        x, gt = _inputs(preset, 2)
+        xc, gc = x.cuda(), gt.cuda()
+        losses = [float(eng.train_step(xc, gc)[0]) for _ in range(3)]
+        torch.cuda.synchronize()
+        outs.append((losses, params["pose_mlp.pose_fcs.0.weight"].cpu(), params["pos_heatmap_encoder.fc1.bn.running_mean"].cpu(),
+                     int(params["pos_heatmap_encoder.fc1.bn.num_batches_tracked"])))
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3] == 3
