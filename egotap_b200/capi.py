@@ -67,7 +67,7 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_fill_dummy": [P, P, I, I, I, P],
         "egotap_b200_pos_permute": [P, P, I, I, P, P, P],
         "egotap_b200_pu_bridge_gate": [P, I, I, P, I, I, LL, P, P, P],
-        "egotap_b200_transpose_split": [P, LL, I, LL, I, I, P, P, LL, P, P, LL, LL, P],
+        "egotap_b200_transpose_split": [P, LL, I, LL, I, I, P, P, LL, P, P, LL, LL, P, P, P, LL, P],
         "egotap_b200_transpose_bf16": [P, P, LL, I, LL, I, LL, I, LL, P, P, LL, LL, LL, LL, P],
         "egotap_b200_colsum": [P, LL, I, LL, I, I, P, P, LL, P],
         "egotap_b200_reduce_partials": [P, I, LL, P, P],
@@ -398,9 +398,11 @@ class CudaBackend:
                                       self._st())
 
     # ---- training ops
-    def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows):
+    def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows,
+                        gelu_u=None, colsum_out=None, scratch=None):
         self._c("egotap_b200_transpose_split", _ptr(src), rows, cols, src_ld, rows_in, rows_out, _ptr(rm_hi), _ptr(rm_lo),
-                                                 rm_ld, _ptr(t_hi), _ptr(t_lo), t_ld, pad_rows, self._st())
+                rm_ld, _ptr(t_hi), _ptr(t_lo), t_ld, pad_rows, _ptr(gelu_u), _ptr(colsum_out), _ptr(scratch),
+                0 if scratch is None else scratch.numel(), self._st())
 
     def transpose_bf16(self, s_hi, s_lo, rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, d_hi, d_lo, d_ld, d_g0s, d_g1s, pad_rows):
         self._c("egotap_b200_transpose_bf16", _ptr(s_hi), _ptr(s_lo), rows, cols, s_ld, g0c, s_g0s, g1c, s_g1s, _ptr(d_hi),

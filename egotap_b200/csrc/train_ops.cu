@@ -40,17 +40,28 @@ inline unsigned blocks_for(long long n, int per_block, long long cap) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// transpose_split: fp32 (rows x cols) -> row-major bf16 pair rm[r][c] and/or transposed pair t[c][r];
-// t[c][rows .. pad_rows) = 0.  Logical row r lives at source row (r/rows_out)*rows_in + r%rows_out (rows_out > 0).
-// 64 x 64 tiles through shared memory; both outputs are written with full-width coalesced stores.
+// transpose_split: the "gradient preparation" pass.  fp32 (rows x cols) -> row-major bf16 pair rm[r][c] and/or
+// transposed pair t[c][r] (t[c][rows .. pad_rows) = 0), optionally with
+//   * gelu_u != null: the value is first multiplied by gelu'(u[r][c]) (u has the source's layout) -- the backward of the
+//     MLP activation fused into the pass that consumes it, so d u is never written in fp32
+//   * colpart != null: per-tile column sums colpart[blockIdx.y][c] (the bias gradient's first reduction stage)
+// Logical row r lives at source row (r/rows_out)*rows_in + r%rows_out (rows_out > 0).
+// 64 x 64 tiles through shared memory; all outputs are written with full-width coalesced stores.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, long long rows, int cols,
                                                               long long src_ld, int rows_in, int rows_out,
                                                               __nv_bfloat16* __restrict__ rm_hi,
                                                               __nv_bfloat16* __restrict__ rm_lo, long long rm_ld,
                                                               __nv_bfloat16* __restrict__ t_hi,
                                                               __nv_bfloat16* __restrict__ t_lo, long long t_ld,
-                                                              long long pad_rows) {
+                                                              long long pad_rows, const float* __restrict__ gelu_u,
+                                                              float* __restrict__ colpart) {
   __shared__ float tile[64][65];
   const int c0 = blockIdx.x * 64;
   const long long r0 = (long long)blockIdx.y * 64;
@@ -62,15 +73,26 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
       const long long r = r0 + rr;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < rows) {
-        v = *reinterpret_cast<const float4*>(src + src_row(r, rows_in, rows_out) * src_ld + c0 + tx * 4);
+        const long long so = src_row(r, rows_in, rows_out) * src_ld + c0 + tx * 4;
+        v = *reinterpret_cast<const float4*>(src + so);
+        if (gelu_u) {
+          const float4 u = *reinterpret_cast<const float4*>(gelu_u + so);
+          v.x *= gelu_grad(u.x); v.y *= gelu_grad(u.y); v.z *= gelu_grad(u.z); v.w *= gelu_grad(u.w);
+        }
         if (rm_hi) st_split4(rm_hi, rm_lo, r * rm_ld + c0 + tx * 4, v);
       }
       tile[rr][tx * 4 + 0] = v.x; tile[rr][tx * 4 + 1] = v.y; tile[rr][tx * 4 + 2] = v.z; tile[rr][tx * 4 + 3] = v.w;
     }
   }
-  if (!t_hi) return;
+  if (!t_hi && !colpart) return;
   __syncthreads();
-  {
+  if (colpart && threadIdx.x < 64 && r0 < rows) {             // rows beyond `rows` hold zeros
+    float acc = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < 64; ++rr) acc += tile[rr][threadIdx.x];
+    colpart[(long long)blockIdx.y * cols + c0 + threadIdx.x] = acc;
+  }
+  if (t_hi) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 row pairs x 8 columns per pass
     const long long r = r0 + tx * 2;
     if (r < pad_rows) {
@@ -87,24 +109,38 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
   }
 }
 
+int reduce_partials_run(const float* partials, int G, long long n, float* out, cudaStream_t st);
+
 int transpose_split_run(const float* src, long long rows, int cols, long long src_ld, int rows_in, int rows_out,
                         __nv_bfloat16* rm_hi, __nv_bfloat16* rm_lo, long long rm_ld, __nv_bfloat16* t_hi,
-                        __nv_bfloat16* t_lo, long long t_ld, long long pad_rows, cudaStream_t st) {
-  EB_REQUIRE(src && (rm_hi || t_hi), "transpose_split: null pointer");
+                        __nv_bfloat16* t_lo, long long t_ld, long long pad_rows, const float* gelu_u, float* colsum_out,
+                        float* scratch, long long scratch_elems, cudaStream_t st) {
+  EB_REQUIRE(src && (rm_hi || t_hi || colsum_out), "transpose_split: null pointer");
   EB_REQUIRE(rows > 0 && cols > 0 && cols % 64 == 0, "transpose_split: cols (%d) must be a positive multiple of 64", cols);
   EB_REQUIRE(src_ld % 4 == 0 && (!rm_hi || rm_ld % 4 == 0), "transpose_split: leading dimensions must be multiples of 4");
+  EB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (!gelu_u || (reinterpret_cast<uintptr_t>(gelu_u) & 15) == 0),
+             "transpose_split: source must be 16-byte aligned");
   long long extent = rows;
   if (t_hi) {
     EB_REQUIRE(pad_rows >= rows && pad_rows % 2 == 0 && t_ld % 2 == 0 && t_ld >= pad_rows,
                "transpose_split: bad padding (rows %lld pad %lld ld %lld)", rows, pad_rows, t_ld);
     extent = pad_rows;
   }
-  const long long gy = (extent + 63) / 64;
+  const long long gy = (extent + 63) / 64, gy_rows = (rows + 63) / 64;
   EB_REQUIRE(gy <= 65535, "transpose_split: too many rows (%lld)", extent);
-  ProfScope prof("transpose_split_kernel", st);
-  EB_LAUNCH_COOP(transpose_split_kernel, dim3(cols / 64, (unsigned)gy), 256, st, src, rows, cols, src_ld, rows_in, rows_out, rm_hi,
-                                                                       rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows);
-  EB_CHECK_LAUNCH("transpose_split_kernel");
+  float* colpart = nullptr;
+  if (colsum_out) {
+    EB_REQUIRE(scratch && gy_rows * (long long)cols <= scratch_elems, "transpose_split: scratch too small for the column sums "
+               "(%lld x %d floats needed)", gy_rows, cols);
+    colpart = gy_rows == 1 ? colsum_out : scratch;
+  }
+  {
+    ProfScope prof("transpose_split_kernel", st);
+    EB_LAUNCH_COOP(transpose_split_kernel, dim3(cols / 64, (unsigned)gy), 256, st, src, rows, cols, src_ld, rows_in, rows_out,
+                   rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows, gelu_u, colpart);
+    EB_CHECK_LAUNCH("transpose_split_kernel");
+  }
+  if (colsum_out && gy_rows > 1) return reduce_partials_run(scratch, int(gy_rows), cols, colsum_out, st);
   return 0;
 }
 
@@ -262,11 +298,6 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float4* __restrict_
     const float4 v = u[i];
     st_split4(hi, lo, i * 4, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)));
   }
-}
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
 }
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(float4* __restrict__ dg, const float4* __restrict__ u, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -687,9 +718,11 @@ using namespace eb;
 // ---- C ABI (include/egotap_b200.h, "training" section) -------------------------------------------------------
 extern "C" int egotap_b200_transpose_split(const float* src, long long rows, int cols, long long src_ld, int rows_in,
                                            int rows_out, void* rm_hi, void* rm_lo, long long rm_ld, void* t_hi, void* t_lo,
-                                           long long t_ld, long long pad_rows, void* stream) {
+                                           long long t_ld, long long pad_rows, const float* gelu_u, float* colsum_out,
+                                           float* scratch, long long scratch_elems, void* stream) {
   return transpose_split_run(src, rows, cols, src_ld, rows_in, rows_out, (__nv_bfloat16*)rm_hi, (__nv_bfloat16*)rm_lo, rm_ld,
-                             (__nv_bfloat16*)t_hi, (__nv_bfloat16*)t_lo, t_ld, pad_rows, (cudaStream_t)stream);
+                             (__nv_bfloat16*)t_hi, (__nv_bfloat16*)t_lo, t_ld, pad_rows, gelu_u, colsum_out, scratch,
+                             scratch_elems, (cudaStream_t)stream);
 }
 extern "C" int egotap_b200_transpose_bf16(const void* s_hi, const void* s_lo, long long rows, int cols, long long s_ld,
                                           int g0_count, long long s_g0_stride, int g1_count, long long s_g1_stride, void* d_hi,

@@ -189,11 +189,13 @@ class TrainEngine:
                      out_f32=self.partials, ldo=k_out, group_rows=n_out)
         self.be.reduce_partials(self.partials, G, n_out * k_out, grad)
 
-    def _tsplit(self, src, rows, cols, src_ld, rm, t, t_ld, rows_in=0, rows_out=0):
-        """fp32 gradient -> row-major pair ``rm`` (rows x cols) and transposed pair ``t`` (cols x t_ld, zero padded)"""
+    def _tsplit(self, src, rows, cols, src_ld, rm, t, t_ld, rows_in=0, rows_out=0, bias=None, gelu_u=None):
+        """fp32 gradient -> row-major pair ``rm`` (rows x cols) and transposed pair ``t`` (cols x t_ld, zero padded);
+        in the same pass: multiply by gelu'(gelu_u) first, and the column sums (bias gradient) into ``bias``"""
         self.be.transpose_split(src, rows, cols, src_ld, rows_in, rows_out,
                                 None if rm is None else rm.hi, None if rm is None else rm.lo, cols,
-                                None if t is None else t.hi, None if t is None else t.lo, t_ld, t_ld)
+                                None if t is None else t.hi, None if t is None else t.lo, t_ld, t_ld,
+                                gelu_u, bias, None if bias is None else self.S["colpart"])
 
     def _tbf16(self, src, rows, cols, src_ld, dst, dst_ld, groups=(1, 0, 1, 0), dst_groups=(0, 0), pad=None):
         g0c, s_g0s, g1c, s_g1s = groups
@@ -326,6 +328,8 @@ class TrainEngine:
         S["dFG1"], S["dG0"], S["dF0"] = f32(RJ, 5 * PUH), f32(RJ, 4 * PUH), f32(RJ, PUH + PUX)
         S["dhg"], S["dc"], S["dgp"] = f32(B, PUH), f32(B, PUH), pair(B, 4 * PUH)
         S["dpos"] = f32(TOK, HID)
+        S["colpart"] = f32(((M + 63) // 64) * MLPD)           # per-tile column sums of transpose_split (bias gradients)
+        S["bias_tmp"] = f32(5 * PUH)
         S["dpose"] = f32(B, self.nj, 3)
         self.x_in, self.gt_in = f32(B, 6 * J, 64, 64), f32(B, self.nj, 3)
         self.batch = B
@@ -460,10 +464,11 @@ class TrainEngine:
         dFG1 = S["dFG1"]
         self._chain_bwd(B, A["FG1"][:, PUH:], 5 * PUH, A["FG1"], 5 * PUH, A["C1"], A["skel"], S["dSkel"],
                         dFG1[:, PUH:], 5 * PUH, dFG1, 5 * PUH, WT["hh1"])
-        be.colsum(dFG1, RJ, PUH, 5 * PUH, 0, 0, g[pu + "1.x2f.bias"], self.scr)
-        be.colsum(dFG1[:, PUH:], RJ, 4 * PUH, 5 * PUH, 0, 0, g[pu + "1.x2h.bias"], self.scr)
-        be.copy(g[pu + "1.h2h.bias"], g[pu + "1.x2h.bias"])
-        self._tsplit(dFG1, RJ, 5 * PUH, 5 * PUH, rm, TA, ldJ)
+        bt = S["bias_tmp"]
+        self._tsplit(dFG1, RJ, 5 * PUH, 5 * PUH, rm, TA, ldJ, bias=bt)
+        be.copy(g[pu + "1.x2f.bias"], bt[:PUH])
+        be.copy(g[pu + "1.x2h.bias"], bt[PUH:])
+        be.copy(g[pu + "1.h2h.bias"], bt[PUH:])
         self._tbf16(A["h0b"], RJ, PUH, PUH, TB, ldJ)
         self._dw(TA, TB, PUH, PUH, RJ, ldJ, g[pu + "1.x2f.weight"])
         self._dw(_rows(TA, PUH, ldJ), TB, 4 * PUH, PUH, RJ, ldJ, g[pu + "1.x2h.weight"])
@@ -473,10 +478,9 @@ class TrainEngine:
         dG0, dF0, dE = S["dG0"], S["dF0"], S["dE"]
         self._chain_bwd(B, A["G0"], 4 * PUH, A["F0"], PUH + PUX, A["C0"], A["H0"], S["dH0"], dG0, 4 * PUH, dF0, PUH + PUX,
                         WT["hh0"])
-        be.colsum(dG0, RJ, 4 * PUH, 4 * PUH, 0, 0, g[pu + "0.x2h.bias"], self.scr)
+        self._tsplit(dG0, RJ, 4 * PUH, 4 * PUH, rm, TA, ldJ, bias=g[pu + "0.x2h.bias"])
         be.copy(g[pu + "0.b2h.bias"], g[pu + "0.x2h.bias"])
         be.copy(g[pu + "0.h2h.bias"], g[pu + "0.x2h.bias"])
-        self._tsplit(dG0, RJ, 4 * PUH, 4 * PUH, rm, TA, ldJ)
         self._tbf16(A["xb"], RJ, 2 * PUX, 2 * PUX, TB, ldJ)
         self._dw(TA, TB, 4 * PUH, PUX, RJ, ldJ, g[pu + "0.x2h.weight"])
         self._dw(TA, _rows(TB, PUX, ldJ), 4 * PUH, PUX, RJ, ldJ, g[pu + "0.b2h.weight"])
@@ -486,8 +490,7 @@ class TrainEngine:
         self._gemm(rm, 4 * PUH, RJ, 4 * PUH, WT["xb0"], 4 * PUH, 2 * PUX, resid=dE, resid_ld=2 * PUX, out_f32=dE,
                    ldo=2 * PUX)
         be.pu_bridge_gate_bwd(dE, 2 * PUX, A["F0"], PUH + PUX, PUH, A["E"], PUX, RJ, dF0, PUH + PUX)
-        be.colsum(dF0, RJ, PUH + PUX, PUH + PUX, 0, 0, g[pu + "0.x2f.bias"], self.scr)
-        self._tsplit(dF0, RJ, PUH + PUX, PUH + PUX, rm, TA, ldJ)
+        self._tsplit(dF0, RJ, PUH + PUX, PUH + PUX, rm, TA, ldJ, bias=g[pu + "0.x2f.bias"])
         self._tbf16(A["xb"], RJ, PUX, 2 * PUX, TB, ldJ)
         self._dw(TA, TB, PUH + PUX, PUX, RJ, ldJ, g[pu + "0.x2f.weight"])
         self._gemm(rm, PUH + PUX, RJ, PUH + PUX, WT["x2f0"], PUH + PUX, PUX, resid=dE, resid_ld=2 * PUX, out_f32=dE,
@@ -503,8 +506,7 @@ class TrainEngine:
                 y = A["%sy%d" % (e, i + 1)]
                 mean, rstd, scale, shift = (A["%s%s%d" % (e, s, i + 1)] for s in ("mean", "rstd", "scale", "shift"))
                 be.bn_bwd(da, y, R, n, scale, shift, mean, rstd, g[pre + "bn.weight"], g[pre + "bn.bias"], self.scr)
-                be.colsum(da, R, n, n, 0, 0, g[pre + "fc.bias"], self.scr)
-                self._tsplit(da, R, n, n, rm, TA, ldR)
+                self._tsplit(da, R, n, n, rm, TA, ldR, bias=g[pre + "fc.bias"])
                 if i == 0:
                     x_in, k = (A["fin"], 16 * HID) if e == "p" else (A["a_limb"], 8192)
                 else:
@@ -528,30 +530,27 @@ class TrainEngine:
             h_in, h_mid = A["h_in"][l], A["h_mid"][l]
             ln1, qk, vt, ctx, ln2, u, gl = (A[n][l] for n in ("ln1", "qk", "vt", "ctx", "ln2", "u", "g"))
             # MLP: h_out = h_mid + down(gelu(up(ln2)))
-            be.colsum(dH, M, HID, HID, 0, 0, g[p + "output.dense.bias"], self.scr)
-            self._tsplit(dH, M, HID, HID, rm, TA, ldM)
+            self._tsplit(dH, M, HID, HID, rm, TA, ldM, bias=g[p + "output.dense.bias"])
             self._tbf16(gl, M, MLPD, MLPD, TB, ldM)
             self._dw(TA, TB, HID, MLPD, M, ldM, g[p + "output.dense.weight"])
             self._gemm(rm, HID, M, HID, WT["down%d" % l], HID, MLPD, out_f32=dA, ldo=MLPD)
-            be.gelu_bwd(dA, u, M * MLPD)
-            be.colsum(dA, M, MLPD, MLPD, 0, 0, g[p + "intermediate.dense.bias"], self.scr)
-            self._tsplit(dA, M, MLPD, MLPD, rm, TA, ldM)
+            # d u = d g * gelu'(u), its bf16 copies and the bias gradient in one pass (d u is never stored in fp32)
+            self._tsplit(dA, M, MLPD, MLPD, rm, TA, ldM, bias=g[p + "intermediate.dense.bias"], gelu_u=u)
             self._tbf16(ln2, M, HID, HID, TB, ldM)
             self._dw(TA, TB, MLPD, HID, M, ldM, g[p + "intermediate.dense.weight"])
             self._gemm(rm, MLPD, M, MLPD, WT["up%d" % l], MLPD, HID, out_f32=dA, ldo=HID)
             be.layernorm_bwd(dA, h_mid, P[p + "layernorm_after.weight"], B, TOK, TOK, LN_EPS, dH, 1,
                              g[p + "layernorm_after.weight"], g[p + "layernorm_after.bias"], self.scr)
             # attention block: h_mid = h_in + o(attn(ln1))
-            be.colsum(dH, M, HID, HID, 0, 0, g[p + "attention.output.dense.bias"], self.scr)
-            self._tsplit(dH, M, HID, HID, rm, TA, ldM)
+            self._tsplit(dH, M, HID, HID, rm, TA, ldM, bias=g[p + "attention.output.dense.bias"])
             self._tbf16(ctx, M, HID, HID, TB, ldM)
             self._dw(TA, TB, HID, HID, M, ldM, g[p + "attention.output.dense.weight"])
             dctx = S["dctx"]
             self._gemm(rm, HID, M, HID, WT["o%d" % l], HID, HID, out=dctx, ldo=HID)
             self._attention_bwd(B, qk, vt, dctx, dA)         # dA <- d[Q | K | V]  (M x 3072)
+            self._tsplit(dA, M, 3 * HID, 3 * HID, rm, TA, ldM, bias=S["dpos"])     # (3072,) sums into a spare buffer
             for q, n in enumerate(("query", "key", "value")):
-                be.colsum(dA[:, q * HID:], M, HID, 3 * HID, 0, 0, g[p + "attention.attention.%s.bias" % n], self.scr)
-            self._tsplit(dA, M, 3 * HID, 3 * HID, rm, TA, ldM)
+                be.copy(g[p + "attention.attention.%s.bias" % n], S["dpos"].view(-1)[q * HID:(q + 1) * HID])
             self._tbf16(ln1, M, HID, HID, TB, ldM)
             for q, n in enumerate(("query", "key", "value")):
                 self._dw(_rows(TA, q * HID, ldM), TB, HID, HID, M, ldM, g[p + "attention.attention.%s.weight" % n])
@@ -562,8 +561,8 @@ class TrainEngine:
         # ---- embeddings: hidden[b, t] = patch_gemm + bias + pos_perm[t] (t < live) | mask_token + pos_perm[t]
         Ml = B * live
         ldL = pad_ld(Ml)
-        be.colsum(dH, Ml, HID, HID, TOK, live, g[v + "embeddings.patch_embeddings.projection.bias"], self.scr)
-        self._tsplit(dH, Ml, HID, HID, None, TA, ldL, rows_in=TOK, rows_out=live)
+        self._tsplit(dH, Ml, HID, HID, None, TA, ldL, rows_in=TOK, rows_out=live,
+                     bias=g[v + "embeddings.patch_embeddings.projection.bias"])
         self._tbf16(A["a_patch"], Ml, 256, 256, TB, ldL)
         self._dw(TA, TB, HID, 256, Ml, ldL, g[v + "embeddings.patch_embeddings.projection.weight"])
         be.colsum(dH, B, TOK * HID, TOK * HID, 0, 0, S["dpos"], self.scr)      # sum over frames per token

@@ -193,11 +193,14 @@ int egotap_b200_pos_permute(const float* pos, const float* mask_token, int grid,
                             void* stream);
 int egotap_b200_pu_bridge_gate(const float* f, int f_ld, int f_col, const float* e, int e_ld, int X, long long rows, void* hi,
                                void* lo, void* stream);
-/* fp32 (rows x cols) -> row-major bf16 pair rm[r][c] and / or transposed pair t[c][r] (t[c][rows..pad_rows) = 0);
- * logical row r is read from source row (r / rows_out) * rows_in + r % rows_out when rows_out > 0 */
+/* gradient preparation: fp32 (rows x cols) -> row-major bf16 pair rm[r][c] and / or transposed pair t[c][r]
+ * (t[c][rows..pad_rows) = 0); logical row r is read from source row (r / rows_out) * rows_in + r % rows_out when
+ * rows_out > 0.  gelu_u (nullable): values are first multiplied by gelu'(gelu_u[r][c]) (same layout as src).
+ * colsum_out (nullable): also out[c] = sum_r value[r][c] (needs scratch of ceil(rows/64) * cols floats). */
 int egotap_b200_transpose_split(const float* src, long long rows, int cols, long long src_ld, int rows_in, int rows_out,
                                 void* rm_hi, void* rm_lo, long long rm_ld, void* t_hi, void* t_lo, long long t_ld,
-                                long long pad_rows, void* stream);
+                                long long pad_rows, const float* gelu_u, float* colsum_out, float* scratch,
+                                long long scratch_elems, void* stream);
 /* batched bf16 transpose d[g1][g0][c][r] = s[g1][g0][r][c], zero padded to pad_rows */
 int egotap_b200_transpose_bf16(const void* s_hi, const void* s_lo, long long rows, int cols, long long s_ld, int g0_count,
                                long long s_g0_stride, int g1_count, long long s_g1_stride, void* d_hi, void* d_lo,

@@ -260,12 +260,21 @@ class OracleBackend:
         r = torch.arange(rows)
         return (r // rows_out) * rows_in + r % rows_out if rows_out > 0 else r
 
-    def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows):
+    def transpose_split(self, src, rows, cols, src_ld, rows_in, rows_out, rm_hi, rm_lo, rm_ld, t_hi, t_lo, t_ld, pad_rows,
+                        gelu_u=None, colsum_out=None, scratch=None):
         """fp32 (rows x cols; logical row r lives at source row (r/rows_out)*rows_in + r%rows_out when rows_out > 0)
-        -> row-major bf16 pair rm[r][c] and/or transposed pair t[c][r], t[c][rows..pad_rows) = 0."""
+        -> row-major bf16 pair rm[r][c] and/or transposed pair t[c][r], t[c][rows..pad_rows) = 0.
+        gelu_u: values are first multiplied by gelu'(gelu_u) (same layout as src); colsum_out[c] = sum_r value[r][c]."""
         self.launches += 1
         sr = self._src_rows(rows, rows_in, rows_out)
-        x = flat(src)[sr.view(-1, 1) * src_ld + torch.arange(cols).view(1, -1)]
+        idx = sr.view(-1, 1) * src_ld + torch.arange(cols).view(1, -1)
+        x = flat(src)[idx]
+        if gelu_u is not None:
+            u = flat(gelu_u)[idx].double()
+            d = 0.5 * (1 + torch.erf(u / math.sqrt(2.0))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+            x = (x.double() * d).float()
+        if colsum_out is not None:
+            flat(colsum_out)[:cols] = x.double().sum(0).float()
         if rm_hi is not None:
             store_pair(rm_hi, rm_lo, torch.arange(rows).view(-1, 1) * rm_ld + torch.arange(cols).view(1, -1), x)
         if t_hi is not None:

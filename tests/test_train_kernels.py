@@ -76,6 +76,16 @@ def test_transpose_split(backends, rows, cols, rows_in, rows_out):
     _same(a[9], b[9])
     a, b = _both(backends, "transpose_split", lambda: args()[:9] + [None, None, 0, 0])
     _same(a[6], b[6])
+    # fused forms: gelu'(u) factor and the column sums (bias gradient), with and without the bf16 outputs
+    u = torch.randn(src_rows, ld) * 2
+    scr = torch.zeros(((rows + 63) // 64) * cols)
+    a, b = _both(backends, "transpose_split", lambda: args() + [u, torch.full((cols,), float("nan")), scr.clone()])
+    for i in (6, 9):
+        _same(a[i].float() + a[i + 1].float(), b[i].float() + b[i + 1].float(), 2e-5)
+    _same(a[14], b[14], 2e-6)
+    a, b = _both(backends, "transpose_split", lambda: args()[:6] + [None, None, 0, None, None, 0, 0, None,
+                                                                    torch.full((cols,), float("nan")), scr.clone()])
+    _same(a[14], b[14], 2e-6)
 
 
 def test_transpose_bf16_grouped(backends):
