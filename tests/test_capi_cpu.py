@@ -151,8 +151,11 @@ def test_training_entries_reject_bad_arguments_without_a_gpu(lib):
     buf = (C.c_float * 64)()
     p = C.cast(buf, C.c_void_p)
     err = lambda: lib.egotap_b200_last_error().decode()
-    assert lib.egotap_b200_transpose_split(p, 128, 65, 128, 0, 0, p, p, 128, None, None, 0, 0, None) < 0 and "cols (65)" in err()
-    assert lib.egotap_b200_transpose_split(p, 128, 64, 64, 0, 0, None, None, 0, p, p, 130, 100, None) < 0 and "rows 128 pad 100 ld 130" in err()
+    assert lib.egotap_b200_transpose_split(p, 128, 65, 128, 0, 0, p, p, 128, None, None, 0, 0, None, None, None, 0, None) < 0 and "cols (65)" in err()
+    assert lib.egotap_b200_transpose_split(p, 128, 64, 64, 0, 0, None, None, 0, p, p, 130, 100, None, None, None, 0, None) < 0 \
+        and "rows 128 pad 100 ld 130" in err()
+    assert lib.egotap_b200_transpose_split(p, 128, 64, 64, 0, 0, p, p, 64, None, None, 0, 0, None, p, p, 100, None) < 0 \
+        and "2 x 64 floats needed" in err()
     assert lib.egotap_b200_transpose_bf16(p, p, 10, 70, 128, 1, 0, 1, 0, p, p, 64, 0, 0, 64, None) < 0 and "cols (70)" in err()
     assert lib.egotap_b200_transpose_bf16(p, p, 10, 64, 128, 1, 0, 1, 0, p, p, 20, 0, 0, 8, None) < 0 and "rows 10 pad 8 ld 20" in err()
     assert lib.egotap_b200_colsum(p, 16, 6, 8, 0, 0, p, p, 64, None) < 0 and "multiples of 4" in err()
