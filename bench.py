@@ -517,7 +517,8 @@ def main():
     ap.add_argument("--impl", default="egotap_b200", choices=["egotap_b200", "reference", "torch_eager"])
     ap.add_argument("--preset", default="UnrealEgo", choices=["UnrealEgo", "EgoCap"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 256 for the lifting workloads, 32 for train)")
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["bf16x3", "bf16"],
+                    help="operand precision (default: bf16x3 = fp32-parity mode for the lifting workloads, bf16 for train)")
     ap.add_argument("--workload", default="lifting", choices=["lifting", "lifting_gt", "e2e_rgb", "train"],
                     help="lifting = BASELINE configs 1-3 (default); lifting_gt = the same with the input heatmaps synthesised on "
                          "the GPU from keypoints each step (--use_gt_heatmap path); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting); "
@@ -527,6 +528,8 @@ def main():
     args = ap.parse_args()
     if args.batch <= 0:
         args.batch = 32 if args.workload == "train" else 256
+    if args.precision is None:
+        args.precision = "bf16" if args.workload == "train" else "bf16x3"
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     if args.workload == "train":
