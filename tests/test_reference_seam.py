@@ -62,3 +62,53 @@ def test_reference_wrapper_accepts_the_swapped_factory(preset, tmp_path, state_d
     with pytest.raises(RuntimeError, match="no CPU path"):
         model.forward(evaluate=True)
     assert model.pred_heatmap_cat.shape == (1, 6 * J, 64, 64)      # the wrapper built our input in its own layout
+
+
+def test_reference_optimize_parameters_trains_our_module(tmp_path, state_dicts):
+    """The reference's own training step, unmodified (`EgoTAPAutoEncoderModel.optimize_parameters`,
+    model/egotap_autoencoder_model.py:299-323: .train(), zero_grad, forward, MPJPE + cos-sim losses, GradScaler,
+    torch.optim.AdamW from model/network.py:72-78), driving OUR module through the swapped factory.  On CPU the module's
+    training engine runs against the op oracle (tests only); the weights after one step must equal the training oracle's."""
+    import op_oracle
+    import train_oracle as tro
+    import gt_heatmap_oracle as gto
+    ref_shim.import_reference()
+    import model.network as ref_network
+    from model.models import create_model
+    import egotap_b200
+    preset = "UnrealEgo"
+    opt = ref_shim.make_opt(preset, isTrain=True, log_dir=str(tmp_path), experiment_name="exp", use_amp=False,
+                            path_to_trained_heatmap=None, model_name="resnet18", init_ImageNet=False, use_gt_heatmap=True,
+                            distributed=False, train_heatmap=False, optimizer_type="AdamW", lr=1e-3, opt_eps=1e-4,
+                            weight_decay=0.0, lr_policy="cos_anneal_warmup", niter=1, niter_decay=15, epoch_iter_cnt=10,
+                            lambda_mpjpe=0.1, lambda_cos_sim=-0.01, epoch_count=1)
+    original = ref_network.define_AutoEncoder
+    ref_network.define_AutoEncoder = egotap_b200.define_AutoEncoder
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            model = create_model(opt)
+    finally:
+        ref_network.define_AutoEncoder = original
+    # every reference training script passes --path_to_trained_heatmap (frozen heatmap nets, train_heatmap False);
+    # there are no such files here, so the wrapper was built without and the flag is set by hand
+    model.train_heatmap = False
+    net = model.net_AutoEncoder
+    sd = state_dicts(preset)
+    net.load_state_dict(sd, strict=True)
+    net._engine_backend = op_oracle.OracleBackend(exact=True)
+    # one frame pair of ground-truth heatmaps (the --use_gt_heatmap path) and a target pose
+    pts2d, pts3d = gto.synthetic_keypoints(preset, 2, seed=3)
+    x = torch.stack([torch.from_numpy(gto.lifting_input(pts2d[b, 0], pts2d[b, 1], pts3d[b, 0], pts3d[b, 0], preset)) for b in range(2)])
+    J = 15
+    model.gt_heatmap_left, model.gt_heatmap_right = x[:, :J], x[:, J:2 * J]
+    model.gt_limb_heatmap_left, model.gt_limb_heatmap_right = x[:, 2 * J:4 * J], x[:, 4 * J:]
+    model.input_rgb_left = model.input_rgb_right = torch.zeros(2, 3, 256, 256)
+    model.gt_pose = torch.randn(2, 16, 3, generator=torch.Generator().manual_seed(4)) * 20
+    model.optimize_parameters()
+    ref_loss, ref_sd, _, _ = tro.train_step(sd, x, model.gt_pose, preset, lr=model.optimizer_AutoEncoder.param_groups[0]["lr"])
+    assert abs(float(model.loss_total) - float(ref_loss)) < 1e-5 * max(1.0, abs(float(ref_loss)))
+    new_sd = net.state_dict()
+    for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.0.h2h.weight",
+              "pos_heatmap_encoder.vit.encoder.layer.1.intermediate.dense.weight", "pos_heatmap_encoder.fc2.bn.running_var"):
+        upd_ref, upd = ref_sd[k] - sd[k], new_sd[k] - sd[k]
+        assert (upd - upd_ref).abs().max().item() <= 2e-2 * upd_ref.abs().max().item() + 2e-7, k
