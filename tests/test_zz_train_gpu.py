@@ -7,7 +7,7 @@ Status note (round 1): these tests were written after the round's GPU budget was
 yet; the host orchestration and the kernels' source are verified on the CPU (tests/test_training_cpu.py,
 tests/test_train_kernels.py[emu]).  The file sorts last so that a failure here cannot mask the inference-path suites.
 
-Tolerances: fp32-parity operand mode (bf16x3): loss to 2e-5, every gradient downstream of the ViT to 2e-3 of its
+Tolerances: fp32-parity operand mode (bf16x3): pose to 1e-3, loss to 1e-4, every gradient downstream of the ViT to 2e-3 of its
 maximum, ViT-side gradients by direction (cos > 0.9995) and norm (2 %) because a 1e-5 forward difference can flip
 single LeakyReLU' factors in front of the first FC block (see tests/test_training_cpu.py); plain-bf16 mode (config 5's
 precision): cos > 0.97 on the tensors carrying the gradient mass."""
@@ -62,8 +62,8 @@ def test_train_step_bf16x3_matches_autograd(preset, batch):
     loss = eng.loss_and_grad(gt.cuda())
     grads = eng.backward()
     torch.cuda.synchronize()
-    assert rel_pose < 5e-4
-    assert abs(float(loss[0]) - float(ref_loss)) < 2e-5 * max(1.0, abs(float(ref_loss)))
+    assert rel_pose < 1e-3                      # the path's stated bound (train-mode BatchNorm sees only 60-90 rows here)
+    assert abs(float(loss[0]) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
     assert not torch.isnan(eng.flat_grad).any()
     worst_rel, worst_cos = 0.0, 1.0
     for k, g_ref in ref_grads.items():
@@ -147,7 +147,7 @@ def test_reference_style_loop_on_the_cuda_module():
     loss.backward()
     opt.step()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(ref_loss)) < 2e-5 * max(1.0, abs(float(ref_loss)))
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
     named = dict(net.named_parameters())
     for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.1.x2h.weight",
               "rot_heatmap_encoder.fc2.fc.weight"):
