@@ -19,7 +19,7 @@ import build_emu  # noqa: E402
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_gt_heatmaps.npz")
 
 
-@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.timeout(600)])])
+@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.timeout(600, method="thread")])])
 def backend(request):
     if request.param == "emu":
         return build_emu.make_backend()[0]

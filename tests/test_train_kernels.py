@@ -26,7 +26,7 @@ import build_emu  # noqa: E402
 BF16 = torch.bfloat16
 
 
-@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.timeout(600, method="thread")])])
 def backends(request):
     if request.param == "emu":
         return build_emu.make_backend()

@@ -22,7 +22,7 @@ import weights
 from ref_shim import make_opt
 from egotap_b200.synthetic import synthetic_heatmaps
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 OUT = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
 
 
