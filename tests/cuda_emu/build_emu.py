@@ -12,6 +12,7 @@ OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
 SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "train_ops.cu"), os.path.join(CSRC, "train_model.cu"),
            os.path.join(CSRC, "gt_heatmap.cu")]
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+CUDA_LIB = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
 
 
 def build(force=False):
@@ -20,8 +21,12 @@ def build(force=False):
     if not force and os.path.isfile(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DEB_HOST_EMU", "-I", HERE, "-I", CUDA_INC, "-I", CSRC,
-           "-o", OUT] + SOURCES
+    # -fsanitize=alignment: every pointer dereference is checked against its type's alignment (float4 / uint4: 16 bytes,
+    # float2 / uint2: 8, packed bf16x2 stores: 4) and aborts on a violation -- the one class of kernel bug that plain x86
+    # execution would forgive and the GPU would not
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DEB_HOST_EMU", "-fsanitize=alignment",
+           "-fno-sanitize-recover=alignment", "-I", HERE, "-I", CUDA_INC, "-I", CSRC, "-o", OUT] + SOURCES + \
+          ["-L", CUDA_LIB, "-Wl,-rpath," + CUDA_LIB, "-lcudart"]     # error-string / event symbols only; no device is touched
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

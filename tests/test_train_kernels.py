@@ -317,3 +317,23 @@ def test_recorded_step_replays_identically(backends):
     assert results[0][0] == results[1][0] and results[0][0][0] != results[0][0][1]
     for k in results[0][1]:
         assert torch.equal(results[0][1][k], results[1][1][k]), k
+
+
+def test_emulation_traps_misaligned_vector_access():
+    """the emulation library is built with -fsanitize=alignment: a float4 access through a pointer that is only 4-byte
+    aligned must abort (run in a subprocess) -- so the green emulated runs above also certify the alignment of every
+    vector load / store the engine's call sites produce"""
+    import subprocess
+    code = (
+        "import ctypes as C, sys; sys.path.insert(0, %r); import build_emu\n"
+        "L = C.CDLL(build_emu.build())\n"
+        "buf = (C.c_float * 64)(); out = (C.c_uint16 * 64)()\n"
+        "base = C.addressof(buf)\n"
+        "L.egotap_b200_gelu_fwd.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]\n"
+        "assert L.egotap_b200_gelu_fwd(base, 16, C.addressof(out), None, None) == 0\n"
+        "print('aligned ok', flush=True)\n"
+        "L.egotap_b200_gelu_fwd(base + 4, 16, C.addressof(out), None, None)\n"
+        "print('misaligned survived', flush=True)\n" % os.path.join(os.path.dirname(__file__), "cuda_emu"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "aligned ok" in r.stdout and "misaligned survived" not in r.stdout and r.returncode != 0, (r.stdout, r.stderr[-400:])
+    assert "misaligned address" in r.stderr
