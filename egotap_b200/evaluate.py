@@ -34,3 +34,27 @@ def compute_metrics(pred_pose, gt_pose, running_average_dict):
     for i in range(mpjpes.shape[0]):
         running_average_dict.update(dict(mpjpe=mpjpes[i], pa_mpjpe=pa_mpjpes[i]))
     return mpjpes, pa_mpjpes
+
+
+def save_predictions(pred_poses, gt_poses, input_paths, save_path, data_dir):
+    """The result files of reference ``utils/evaluate.py:127-144`` (``test_evaluate(save_result=True)``), byte for byte:
+    ``pred_pose.npy`` (N, num_joints, 3) fp32 in ``save_path``; ``gt_<dataset>_pose.npy`` and ``input_<dataset>_paths.npy``
+    one directory up; ``input_paths.pkl``.  ``pred_poses`` / ``gt_poses``: per-batch arrays or tensors (cm);
+    ``input_paths``: per-batch sequences of frame paths."""
+    import os
+    import pickle
+
+    import numpy as np
+
+    def host(a):
+        return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    pred = np.concatenate([host(p) for p in pred_poses], axis=0)
+    gt = np.concatenate([host(g) for g in gt_poses], axis=0)
+    paths = np.concatenate([np.asarray(p) for p in input_paths], axis=0).reshape(-1, 1)
+    name = os.path.normpath(data_dir).split("/")[-1].lower()
+    np.save(os.path.join(save_path, "pred_pose.npy"), pred)
+    np.save(os.path.join(save_path, os.pardir, "gt_{}_pose.npy".format(name)), gt)
+    np.save(os.path.join(save_path, os.pardir, "input_{}_paths.npy".format(name)), paths)
+    with open(os.path.join(save_path, "input_paths.pkl"), "wb") as f:
+        pickle.dump(paths, f)
+    return pred, gt, paths

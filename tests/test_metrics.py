@@ -71,3 +71,34 @@ def test_kernel_matches_reference_golden():
     m, pa = pose_metrics(torch.from_numpy(d["pred"]).cuda(), torch.from_numpy(d["gt"]).cuda())
     np.testing.assert_allclose(m.cpu().numpy(), d["mpjpe_mm"], rtol=1e-5, atol=2e-4)
     np.testing.assert_allclose(pa.cpu().numpy(), d["pa_mpjpe_mm"], rtol=1e-5, atol=2e-4)
+
+
+def test_saved_result_files_are_byte_compatible(tmp_path):
+    """pred_pose.npy / gt_<dataset>_pose.npy / input_<dataset>_paths.npy / input_paths.pkl exactly as the reference's
+    test_evaluate(save_result=True) writes them (utils/evaluate.py:127-144)"""
+    import io
+    import os
+    import pickle
+
+    import numpy as np
+    from egotap_b200.evaluate import save_predictions
+    rng = np.random.default_rng(0)
+    preds = [rng.normal(size=(4, 16, 3)).astype(np.float32), rng.normal(size=(3, 16, 3)).astype(np.float32)]
+    gts = [rng.normal(size=(4, 16, 3)).astype(np.float32), rng.normal(size=(3, 16, 3)).astype(np.float32)]
+    paths = [["/d/a/%d.npy" % i for i in range(4)], ["/d/b/%d.npy" % i for i in range(3)]]
+    save = tmp_path / "exp" / "results"
+    save.mkdir(parents=True)
+    save_predictions([torch.from_numpy(p) for p in preds], gts, paths, str(save), "/data/UnrealEgoData/")
+    # the reference's statements, restated
+    want_pred, want_gt = np.concatenate(preds, 0), np.concatenate(gts, 0)
+    want_paths = np.concatenate(paths, 0).reshape(-1, 1)
+
+    def npy_bytes(a):
+        b = io.BytesIO()
+        np.save(b, a)
+        return b.getvalue()
+    assert (save / "pred_pose.npy").read_bytes() == npy_bytes(want_pred)
+    assert (save.parent / "gt_unrealegodata_pose.npy").read_bytes() == npy_bytes(want_gt)
+    assert (save.parent / "input_unrealegodata_paths.npy").read_bytes() == npy_bytes(want_paths)
+    assert pickle.load(open(save / "input_paths.pkl", "rb")).tolist() == want_paths.tolist()
+    assert np.load(save / "pred_pose.npy").shape == (7, 16, 3)
