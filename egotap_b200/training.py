@@ -204,7 +204,6 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------------ weights
     def _alloc_weights(self):
-        J = self.J
         mk = self._pair
         self.W, self.WT = {}, {}
 
@@ -433,7 +432,7 @@ class TrainEngine:
     def backward(self, dpose=None, on_stage=None):
         """gradients of every parameter for the last forward, given d loss / d pose (default: loss_and_grad's).
         on_stage(i, start, end) is called as soon as flat_grad[start:end] is final (in stream order)."""
-        be, P, A, S, W, WT, J, g = self.be, self.P, self.A, self.S, self.W, self.WT, self.J, self.grad
+        be, P, A, S, WT, J, g = self.be, self.P, self.A, self.S, self.WT, self.J, self.grad
         B = self.batch
         M, R, RJ, live = B * TOK, B * self.n_hm, B * J, self.live
         ldM, ldR, ldJ = pad_ld(M), pad_ld(R), pad_ld(RJ)
@@ -586,7 +585,6 @@ class TrainEngine:
         be, S = self.be, self.S
         scale = 1.0 / math.sqrt(HD)
         Bc = min(B, self.attn_chunk)
-        hg = (HEADS, HD, 0, 0)
         for b0 in range(0, B, Bc):
             nb = min(Bc, B - b0)
             G = nb * HEADS

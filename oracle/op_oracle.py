@@ -121,10 +121,9 @@ class OracleBackend:
             return x[:, :want_rows]
         A = operand(a_hi, a_lo, lda or K, a_rows or M, a_group, M)
         B = operand(b_hi, b_lo, ldb or K, b_rows or N, b_group, N)
-        if precision == PREC_BF16X3:        # Ah*Bh + Ah*Bl + Al*Bh: the Al*Bl term is dropped (2^-16 relative)
-            acc = torch.matmul(A, B.transpose(1, 2))
-        else:
-            acc = torch.matmul(A, B.transpose(1, 2))
+        # bf16x3 on the GPU is Ah*Bh + Ah*Bl + Al*Bh (the Al*Bl term, 2^-16 relative, is dropped); here the full
+        # (Ah + Al)(Bh + Bl) product in fp32 stands for it
+        acc = torch.matmul(A, B.transpose(1, 2))
         v = acc * float(epi.pop("alpha", 1.0))
         scale, bias, resid = epi.pop("scale", None), epi.pop("bias", None), epi.pop("resid", None)
         act = int(epi.pop("act", 0))
