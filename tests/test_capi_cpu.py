@@ -171,3 +171,27 @@ def test_training_entries_reject_bad_arguments_without_a_gpu(lib):
     assert lib.egotap_b200_head_bwd(p, p, 512, p, p, p, 4, 15, p, 512, p, p, p, None, None, p, 64, None) < 0 and "dWg" in err()
     assert lib.egotap_b200_embed_grads(p, 5, 30, p, p, None) < 0 and "geometry" in err()
     assert lib.egotap_b200_regroup_gather(p, 512, 2, 4, 15, 128, p, None) < 0 and "multiples of 4" in err()
+
+
+def test_training_and_synthesis_have_no_cpu_path():
+    """the product never falls back: without a CUDA device the training engine and the heatmap synthesis raise"""
+    import weights
+    from egotap_b200 import training
+    from egotap_b200.gt_heatmaps import synthesize
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less host")
+    sd = weights.make_state_dict("UnrealEgo", seed=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        training.TrainEngine("UnrealEgo", {k: v.clone() for k, v in sd.items()})
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        synthesize(torch.zeros(1, 2, 16, 2), torch.zeros(1, 16, 3), "UnrealEgo")
+    import egotap_b200
+    net = egotap_b200.EgoTAPAutoEncoder(make_opt("UnrealEgo"), input_channel_scale=2).train()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        net(torch.zeros(2, net.channels_heatmap, 64, 64))
+    # nothing under egotap_b200/ imports the oracle
+    pkg = os.path.join(ROOT, "egotap_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+(op_oracle|egotap_oracle|train_oracle|gt_heatmap_oracle|metrics_oracle)", src, re.M), f
