@@ -558,6 +558,13 @@ struct AdamTable {
   long long n[64];
 };
 
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float decay, float beta1, float omb1,
+                                          float beta2, float omb2, float step, float inv_sqrt_bc2, float eps) {
+  m = beta1 * m + omb1 * g;
+  v = beta2 * v + omb2 * g * g;
+  p = p * decay - step * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, float beta1, float omb1, float beta2,
                                                     float omb2, float step, float inv_sqrt_bc2, float eps, float grad_scale) {
   const int k = blockIdx.y;
@@ -566,13 +573,27 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamTable tab, float decay, 
   float* __restrict__ m = tab.m[k];
   float* __restrict__ v = tab.v[k];
   const long long n = tab.n[k];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    const float mi = beta1 * m[i] + omb1 * gi;
-    const float vi = beta2 * v[i] + omb2 * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = p[i] * decay - step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  // 16-byte vector body (every tensor's slot in the flat gradient / state buffers is 256-byte aligned; torch aligns
+  // parameter storage), scalar tail
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = tid; i < n4; i += nthreads) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    adamw_one(pp.x, gg.x * grad_scale, mm.x, vv.x, decay, beta1, omb1, beta2, omb2, step, inv_sqrt_bc2, eps);
+    adamw_one(pp.y, gg.y * grad_scale, mm.y, vv.y, decay, beta1, omb1, beta2, omb2, step, inv_sqrt_bc2, eps);
+    adamw_one(pp.z, gg.z * grad_scale, mm.z, vv.z, decay, beta1, omb1, beta2, omb2, step, inv_sqrt_bc2, eps);
+    adamw_one(pp.w, gg.w * grad_scale, mm.w, vv.w, decay, beta1, omb1, beta2, omb2, step, inv_sqrt_bc2, eps);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += nthreads) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adamw_one(pi, g[i] * grad_scale, mi, vi, decay, beta1, omb1, beta2, omb2, step, inv_sqrt_bc2, eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 

@@ -252,7 +252,7 @@ def test_head_bwd_embed_grads_loss_adamw(backends, preset, J, B):
     a, b = _both(backends, "pose_loss", lambda: [pred, gt, B, nj, training.KINEMATIC_PARENTS[preset], not gh, 0.1, -0.01,
                                                   torch.zeros(4), torch.zeros(B, nj, 3), scr])
     _same(a[8][:3], b[8][:3], 1e-5); _same(a[9], b[9], 1e-5)
-    ps = [torch.randn(n) for n in (3, 1000, 70001)]
+    ps = [torch.randn(n) for n in (3, 1000, 70001)] + [torch.randn(1001)[1:]]      # last: 4-byte aligned only -> scalar path
     gs, ms, vs = [torch.randn_like(p) for p in ps], [torch.rand_like(p) * 0.1 for p in ps], [torch.rand_like(p) * 0.01 for p in ps]
     a, b = _both(backends, "adamw", lambda: [[p.clone() for p in ps], gs, [m.clone() for m in ms], [v.clone() for v in vs], 3, 1e-3,
                                               0.9, 0.999, 1e-4, 0.01])
