@@ -7,9 +7,9 @@ Status note (round 1): these tests were written after the round's GPU budget was
 yet; the host orchestration and the kernels' source are verified on the CPU (tests/test_training_cpu.py,
 tests/test_train_kernels.py[emu]).  The file sorts last so that a failure here cannot mask the inference-path suites.
 
-Tolerances: fp32-parity operand mode (bf16x3): pose to 1e-3, loss to 1e-4, every gradient downstream of the ViT to 2e-3 of its
-maximum, ViT-side gradients by direction (cos > 0.9995) and norm (2 %) because a 1e-5 forward difference can flip
-single LeakyReLU' factors in front of the first FC block (see tests/test_training_cpu.py); plain-bf16 mode (config 5's
+Tolerances: fp32-parity operand mode (bf16x3): pose to 1e-3, loss to 1e-4, the gradients downstream of every LeakyReLU
+(head, propagation chain) to 2e-3 of their maximum, FC-encoder and ViT gradients by direction (cos > 0.9995) and norm
+(2 %) because a 1e-5 forward difference can flip single LeakyReLU' factors at z ~ 0 (see tests/test_training_cpu.py); plain-bf16 mode (config 5's
 precision): cos > 0.97 on the tensors carrying the gradient mass."""
 import json
 import os
@@ -70,7 +70,7 @@ def test_train_step_bf16x3_matches_autograd(preset, batch):
         if g_ref is None or g_ref.abs().max() < 1e-7:
             continue
         g = grads[k].cpu()
-        upstream = "vit." in k or k.startswith("pos_heatmap_encoder.fc1")
+        upstream = "heatmap_encoder" in k          # anything at or upstream of a LeakyReLU (all six FC blocks, the ViT)
         if not upstream:
             err, scale = (g - g_ref).abs().max().item(), g_ref.abs().max().item()
             worst_rel = max(worst_rel, err / scale)
@@ -87,7 +87,7 @@ def test_train_step_bf16x3_matches_autograd(preset, batch):
     eng.adamw_step(lr=1e-3, eps=1e-4)
     torch.cuda.synchronize()
     for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.0.h2h.weight",
-              "rot_heatmap_encoder.fc1.fc.weight"):
+              "skel_sequential_layer.lstm_custom.layers.1.x2f.bias"):
         upd_ref, upd = ref_sd[k] - sd[k], params[k].cpu() - sd[k]
         assert (upd - upd_ref).abs().max().item() <= 3e-2 * upd_ref.abs().max().item() + 2e-7, k
     _record("train_step_bf16x3[%s]" % preset, dict(rel_pose=rel_pose, worst_rel_downstream=worst_rel, worst_cos=worst_cos,
@@ -150,9 +150,11 @@ def test_reference_style_loop_on_the_cuda_module():
     assert abs(float(loss) - float(ref_loss)) < 1e-4 * max(1.0, abs(float(ref_loss)))
     named = dict(net.named_parameters())
     for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.1.x2h.weight",
-              "rot_heatmap_encoder.fc2.fc.weight"):
+              "skel_sequential_layer.lstm_custom.layers.0.b2h.weight"):
         g_ref = ref_grads[k]
         assert (named[k].grad.cpu() - g_ref).abs().max().item() <= 2e-3 * g_ref.abs().max().item() + 1e-7, k
+    for k in ("rot_heatmap_encoder.fc2.fc.weight", "pos_heatmap_encoder.vit.encoder.layer.1.attention.output.dense.weight"):
+        assert _cos(named[k].grad, ref_grads[k]) > 0.9995, k
     assert named["pos_heatmap_encoder.vit.embeddings.cls_token"].grad is None
     # and back to inference with the updated weights: the eval path re-packs
     net.eval()
