@@ -89,7 +89,7 @@ def test_train_step_bf16x3_matches_autograd(preset, batch):
     for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.0.h2h.weight",
               "skel_sequential_layer.lstm_custom.layers.1.x2f.bias"):
         upd_ref, upd = ref_sd[k] - sd[k], params[k].cpu() - sd[k]
-        assert (upd - upd_ref).abs().max().item() <= 3e-2 * upd_ref.abs().max().item() + 2e-7, k
+        assert (upd - upd_ref).abs().max().item() <= 5e-2 * upd_ref.abs().max().item() + 2e-7, k
     _record("train_step_bf16x3[%s]" % preset, dict(rel_pose=rel_pose, worst_rel_downstream=worst_rel, worst_cos=worst_cos,
                                                     loss=float(loss[0]), ref_loss=float(ref_loss)))
 
