@@ -3,7 +3,11 @@
 // All are coalesced, 16-byte vectorised where the layout allows, and sized in multiples of the SM count.
 #include "host_util.cuh"
 #include "internal.h"
+#ifdef EB_HOST_EMU          // CUDA-on-CPU emulation of the tests (tests/cuda_emu): no inline PTX
+#include "numeric.cuh"
+#else
 #include "ptx.cuh"
+#endif
 
 namespace eb {
 
@@ -51,7 +55,7 @@ int split2d_run(const float* src, long long rows, long long cols, long long src_
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope prof("split2d_kernel", stream);
-  split2d_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, rows, int(cols / 4), src_ld, hi, lo, dst_ld);
+  EB_LAUNCH(split2d_kernel, (unsigned)blocks, 256, stream, src, rows, int(cols / 4), src_ld, hi, lo, dst_ld);
   EB_CHECK_LAUNCH("split2d_kernel");
   return 0;
 }
@@ -100,7 +104,7 @@ int ingest_run(const float* x, int B, int J, __nv_bfloat16* p_hi, __nv_bfloat16*
                __nv_bfloat16* l_lo, cudaStream_t stream) {
   EB_REQUIRE(x && p_hi && l_hi && B > 0, "ingest: bad arguments");
   ProfScope prof("ingest_kernel", stream);
-  ingest_kernel<<<B * 6 * J, 256, 0, stream>>>(x, J, p_hi, p_lo, l_hi, l_lo);
+  EB_LAUNCH(ingest_kernel, B * 6 * J, 256, stream, x, J, p_hi, p_lo, l_hi, l_lo);
   EB_CHECK_LAUNCH("ingest_kernel");
   return 0;
 }
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(256) fill_dummy_kernel(float4* __restrict__ hi
 int fill_dummy_run(float* hidden, const float* dummy, int B, int tokens, int live, cudaStream_t stream) {
   if (tokens == live) return 0;
   ProfScope prof("fill_dummy_kernel", stream);
-  fill_dummy_kernel<<<B * (tokens - live), 256, 0, stream>>>((float4*)hidden, (const float4*)dummy, tokens, live);
+  EB_LAUNCH(fill_dummy_kernel, B * (tokens - live), 256, stream, (float4*)hidden, (const float4*)dummy, tokens, live);
   EB_CHECK_LAUNCH("fill_dummy_kernel");
   return 0;
 }
@@ -176,7 +180,7 @@ int layernorm_run(const float* x, const float* w, const float* b, long long fram
   const long long out_rows = frames * rows_out;
   if (out_rows == 0) return 0;
   ProfScope prof("layernorm1024_kernel", stream);
-  layernorm1024_kernel<<<(unsigned)((out_rows + 7) / 8), 256, 0, stream>>>(x, w, b, out_rows, rows_in, rows_out, eps, hi,
+  EB_LAUNCH_COOP(layernorm1024_kernel, (unsigned)((out_rows + 7) / 8), 256, stream, x, w, b, out_rows, rows_in, rows_out, eps, hi,
                                                                          lo, out_f32);
   EB_CHECK_LAUNCH("layernorm1024_kernel");
   return 0;
@@ -226,7 +230,7 @@ int softmax_run(const float* s, long long rows, int cols, __nv_bfloat16* hi, __n
   EB_REQUIRE(cols == 576, "softmax: only 576 columns (24x24 tokens) are compiled, got %d", cols);
   if (rows == 0) return 0;
   ProfScope prof("softmax_rows_kernel", stream);
-  softmax_rows_kernel<9><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(s, rows, hi, lo);
+  EB_LAUNCH_COOP(softmax_rows_kernel<9>, (unsigned)((rows + 7) / 8), 256, stream, s, rows, hi, lo);
   EB_CHECK_LAUNCH("softmax_rows_kernel");
   return 0;
 }
@@ -258,7 +262,7 @@ int pu_bridge_gate_run(const float* f, int f_ld, int f_col, const float* e, int 
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof("pu_bridge_gate_kernel", stream);
-  pu_bridge_gate_kernel<<<(unsigned)blocks, 256, 0, stream>>>(f, f_ld, f_col, e, e_ld, X, rows, hi, lo);
+  EB_LAUNCH(pu_bridge_gate_kernel, (unsigned)blocks, 256, stream, f, f_ld, f_col, e, e_ld, X, rows, hi, lo);
   EB_CHECK_LAUNCH("pu_bridge_gate_kernel");
   return 0;
 }
@@ -313,7 +317,7 @@ int pu_cell_run(const float* gates, long long gates_ld, float* c, const float* F
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   ProfScope prof("pu_cell_kernel", stream);
-  pu_cell_kernel<<<(unsigned)blocks, 256, 0, stream>>>(gates, gates_ld, c, F, F_ld, t, J, H, B, out, out_hi, out_lo, hg_hi,
+  EB_LAUNCH(pu_cell_kernel, (unsigned)blocks, 256, stream, gates, gates_ld, c, F, F_ld, t, J, H, B, out, out_hi, out_lo, hg_hi,
                                                       hg_lo);
   EB_CHECK_LAUNCH("pu_cell_kernel");
   return 0;
@@ -373,7 +377,7 @@ int head_run(const float* e, int e_ld, const float* skel, const float* Wp, const
   EB_REQUIRE(e && skel && Wp && bp && pose, "head: null pointer");
   if (B == 0) return 0;
   ProfScope prof("head_kernel", stream);
-  head_kernel<<<(unsigned)B, 256, 0, stream>>>(e, e_ld, skel, Wp, bp, Wg, bg, J, X, H, pose);
+  EB_LAUNCH_COOP(head_kernel, (unsigned)B, 256, stream, e, e_ld, skel, Wp, bp, Wg, bg, J, X, H, pose);
   EB_CHECK_LAUNCH("head_kernel");
   return 0;
 }
@@ -394,7 +398,7 @@ __global__ void bn_fold_kernel(const float* fcb, const float* gamma, const float
 int bn_fold_run(const float* fcb, const float* gamma, const float* beta, const float* mean, const float* var, int n,
                 float* scale, float* shift, cudaStream_t stream) {
   ProfScope prof("bn_fold_kernel", stream);
-  bn_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(fcb, gamma, beta, mean, var, n, 1e-5f, scale, shift);
+  EB_LAUNCH(bn_fold_kernel, (n + 255) / 256, 256, stream, fcb, gamma, beta, mean, var, n, 1e-5f, scale, shift);
   EB_CHECK_LAUNCH("bn_fold_kernel");
   return 0;
 }
@@ -407,7 +411,7 @@ __global__ void vec_add3_kernel(const float* a, const float* b, const float* c, 
 }
 int vec_add3_run(const float* a, const float* b, const float* c, float* out, int n, cudaStream_t stream) {
   ProfScope prof("vec_add3_kernel", stream);
-  vec_add3_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, c, out, n);
+  EB_LAUNCH(vec_add3_kernel, (n + 255) / 256, 256, stream, a, b, c, out, n);
   EB_CHECK_LAUNCH("vec_add3_kernel");
   return 0;
 }
@@ -430,7 +434,7 @@ __global__ void pos_permute_kernel(const float* __restrict__ pos, const float* _
 int pos_permute_run(const float* pos, const float* mask_token, int grid, int n_hm, float* pos_perm, float* dummy,
                     cudaStream_t stream) {
   ProfScope prof("pos_permute_kernel", stream);
-  pos_permute_kernel<<<grid * grid * 16, 256, 0, stream>>>(pos, mask_token, grid, n_hm, pos_perm, dummy);
+  EB_LAUNCH(pos_permute_kernel, grid * grid * 16, 256, stream, pos, mask_token, grid, n_hm, pos_perm, dummy);
   EB_CHECK_LAUNCH("pos_permute_kernel");
   return 0;
 }

@@ -60,6 +60,17 @@ inline float emu_bf16_float(uint32_t b) {
   return x;
 }
 inline uint32_t cvt_bf16x2(float x0, float x1) { return emu_bf16_bits(x0) | (emu_bf16_bits(x1) << 16); }
+inline void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  const uint16_t h = uint16_t(emu_bf16_bits(x)), l = uint16_t(emu_bf16_bits(x - emu_bf16_float(h)));
+  memcpy(&hi, &h, 2);
+  memcpy(&lo, &l, 2);
+}
+inline uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  uint16_t x, y;
+  memcpy(&x, &a, 2);
+  memcpy(&y, &b, 2);
+  return uint32_t(x) | (uint32_t(y) << 16);
+}
 inline void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   hi = cvt_bf16x2(x0, x1);
   lo = cvt_bf16x2(x0 - emu_bf16_float(hi & 0xffffu), x1 - emu_bf16_float(hi >> 16));

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "egotap_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
-SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "train_ops.cu"), os.path.join(CSRC, "train_model.cu"),
+SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "train_ops.cu"),
+           os.path.join(CSRC, "train_model.cu"),
            os.path.join(CSRC, "gt_heatmap.cu")]
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
 CUDA_LIB = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
@@ -35,9 +36,10 @@ def build(force=False):
 
 
 def make_backend():
-    """A backend for training.TrainEngine whose TRAINING ops execute the real kernel source on the CPU emulation, and
-    whose round-1 ops (tcgen05 GEMM, fused attention, LayerNorm, ingest, head, packing kernels: GPU-verified, not
-    emulatable) are served by the op oracle."""
+    """A backend for training.TrainEngine whose bandwidth-bound ops -- the training kernels and the round-1 kernels of
+    csrc/kernels.cu (ingest, LayerNorm, head, packing) -- execute the real kernel source on the CPU emulation; the
+    tensor-core kernels (tcgen05 GEMM, fused attention: GPU-verified in round 1, not emulatable) are served by the op
+    oracle."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import op_oracle
@@ -48,6 +50,10 @@ def make_backend():
     lib.egotap_b200_launch_count.restype = C.c_longlong
     for name, args in capi._TRAIN_ARGTYPES(C.c_void_p, C.c_longlong, C.c_int, C.c_float).items():
         getattr(lib, name).argtypes = args
+    P, I = C.c_void_p, C.c_int
+    lib.egotap_b200_ingest.argtypes = [P, I, I] + [P] * 5
+    lib.egotap_b200_layernorm.argtypes = [P] * 3 + [C.c_longlong, I, I, C.c_float] + [P] * 4
+    lib.egotap_b200_head.argtypes = [P, I] + [P] * 5 + [C.c_longlong, I, P, P]
 
     def check(rc, what):
         if rc != 0:
@@ -78,17 +84,10 @@ def make_backend():
             if self._tape is not None:
                 self._tape.append((lambda: fn(*a, **k), (), None))
 
-        # round-1 ops: oracle
+        # the tensor-core kernels cannot be emulated: oracle.  Everything else (round-1 bandwidth kernels of
+        # csrc/kernels.cu included) runs the real kernel source through the inherited CudaBackend methods.
         def gemm(self, *a, **k): self._py(orc.gemm, *a, **k)
-        def split2d(self, *a): self._py(orc.split2d, *a)
-        def ingest(self, *a): self._py(orc.ingest, *a)
-        def fill_dummy(self, *a): self._py(orc.fill_dummy, *a)
-        def pos_permute(self, *a): self._py(orc.pos_permute, *a)
-        def layernorm(self, *a): self._py(orc.layernorm, *a)
         def attention(self, *a): self._py(orc.attention, *a)
-        def pu_bridge_gate(self, *a): self._py(orc.pu_bridge_gate, *a)
-        def head(self, *a): self._py(orc.head, *a)
-        def add3(self, *a): self._py(orc.add3, *a)
 
     return EmuBackend(), orc
 

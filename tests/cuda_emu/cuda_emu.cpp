@@ -135,12 +135,28 @@ void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>
 namespace eb {
 bool& prof_on() { static bool off = false; return off; }
 void prof_push(const ProfRec&) {}
-static int not_emulated(const char* what) { return fail(EGOTAP_E_UNSUPPORTED, "%s is not part of the CPU emulation", what); }
-int split2d_run(const float*, long long, long long, long long, __nv_bfloat16*, __nv_bfloat16*, long long, cudaStream_t) { return not_emulated("split2d"); }
-int fill_dummy_run(float*, const float*, int, int, int, cudaStream_t) { return not_emulated("fill_dummy"); }
-int pos_permute_run(const float*, const float*, int, int, float*, float*, cudaStream_t) { return not_emulated("pos_permute"); }
-int pu_bridge_gate_run(const float*, int, int, const float*, int, int, long long, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t) { return not_emulated("pu_bridge_gate"); }
-int vec_add3_run(const float*, const float*, const float*, float*, int, cudaStream_t) { return not_emulated("add3"); }
+// declared locally in plan.cu (which holds the tensor-core plan and cannot be emulated)
+int ingest_run(const float*, int, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
+int layernorm_run(const float*, const float*, const float*, long long, int, int, float, __nv_bfloat16*, __nv_bfloat16*,
+                  float*, cudaStream_t);
+int head_run(const float*, int, const float*, const float*, const float*, const float*, const float*, long long, int, int,
+             int, float*, cudaStream_t);
 }  // namespace eb
 extern "C" const char* egotap_b200_last_error(void) { return eb::err_buf(); }
 extern "C" long long egotap_b200_launch_count(void) { return eb::launch_counter().load(); }
+
+// the op-level entries whose extern "C" wrappers live in plan.cu: same one-line forwarding as there
+extern "C" int egotap_b200_ingest(const float* x, int frames, int preset, void* p_hi, void* p_lo, void* l_hi, void* l_lo,
+                                  void* stream) {
+  return eb::ingest_run(x, frames, preset == EGOTAP_PRESET_UNREALEGO ? 15 : 17, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
+                        (__nv_bfloat16*)l_hi, (__nv_bfloat16*)l_lo, (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_layernorm(const float* x, const float* w, const float* b, long long frames, int rows_in,
+                                     int rows_out, float eps, void* hi, void* lo, float* out_f32, void* stream) {
+  return eb::layernorm_run(x, w, b, frames, rows_in, rows_out, eps, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, out_f32,
+                           (cudaStream_t)stream);
+}
+extern "C" int egotap_b200_head(const float* e, int e_ld, const float* skel, const float* Wp, const float* bp,
+                                const float* Wg, const float* bg, long long frames, int J, float* pose, void* stream) {
+  return eb::head_run(e, e_ld, skel, Wp, bp, Wg, bg, frames, J, 256, 512, pose, (cudaStream_t)stream);
+}

@@ -287,7 +287,9 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
         assert cos > 0.999, (k, cos)
         assert abs(float(a.norm() / b.norm()) - 1) < 3e-2, k
     eng.adamw_step()
-    for k in ("pose_mlp.pose_fcs.0.weight", "pos_heatmap_encoder.vit.encoder.layer.1.output.dense.weight"):
+    # AdamW turns every gradient into a step of ~ +-lr, so the update is compared only downstream of the LeakyReLUs
+    # (a single flipped LeakyReLU' factor at z ~ 0 legitimately moves ViT-side steps by O(lr))
+    for k in ("pose_mlp.pose_fcs.0.weight", "skel_sequential_layer.lstm_custom.layers.1.h2h.weight"):
         upd_ref, upd = ref_sd[k] - sd[k], params[k] - sd[k]
         assert (upd - upd_ref).abs().max().item() <= 5e-2 * upd_ref.abs().max().item() + 2e-7, k
 
@@ -337,3 +339,44 @@ def test_emulation_traps_misaligned_vector_access():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "aligned ok" in r.stdout and "misaligned survived" not in r.stdout and r.returncode != 0, (r.stdout, r.stderr[-400:])
     assert "misaligned address" in r.stderr
+
+
+@pytest.mark.parametrize("preset,J", [("UnrealEgo", 15), ("EgoCap", 17)])
+def test_round1_bandwidth_kernels(backends, preset, J):
+    """the round-1 kernels of csrc/kernels.cu that the training engine reuses (ingest, LayerNorm with row compaction,
+    regression head, packing helpers): same vehicles, same oracle"""
+    torch.manual_seed(11)
+    B = 2
+    x = torch.rand(B, 6 * J, 64, 64)
+    a, b = _both(backends, "ingest", lambda: [x, J, *_pair(B * 2 * J * 16, 256), *_pair(B * 2 * J, 8192)])
+    for i in (2, 3, 4, 5):
+        _same(a[i], b[i])
+    h = torch.randn(B * 576, 1024) * 2 + 0.5
+    w, bias = torch.rand(1024) + 0.5, torch.randn(1024) * 0.1
+    live = 2 * J * 16
+    a, b = _both(backends, "layernorm", lambda: [h, w, bias, B, 576, live, 1e-12, *_pair(B * live, 1024),
+                                                 torch.full((B * live, 1024), float("nan"))])
+    _same(a[9], b[9], 2e-6)
+    _same(a[7].float() + a[8].float(), b[7].float() + b[8].float(), 2e-5)
+    e, skel = torch.randn(B * J, 512), torch.randn(B * J, 512)
+    Wp, bp = torch.randn(3, 768), torch.randn(3)
+    gh = preset == "UnrealEgo"
+    Wg, bg = (torch.randn(6, J * 512), torch.randn(6)) if gh else (None, None)
+    a, b = _both(backends, "head", lambda: [e, 512, skel, Wp, bp, Wg, bg, B, J, torch.full((B, J + 1 if gh else J, 3), float("nan"))])
+    _same(a[9], b[9], 1e-5)
+    pos, mask = torch.randn(1, 576, 1024), torch.randn(1, 1, 1024)
+    a, b = _both(backends, "pos_permute", lambda: [pos, mask, 6, 2 * J, torch.full((576, 1024), float("nan")),
+                                                   torch.full((576 - live, 1024), float("nan"))])
+    _same(a[4], b[4]); _same(a[5], b[5], 1e-6)
+    hid = torch.randn(B * 576, 1024)
+    a, b = _both(backends, "fill_dummy", lambda: [hid.clone(), b[5], B, 576, live])
+    _same(a[0], b[0])
+    F0, E = torch.randn(B * J, 768), torch.randn(B * J, 512)
+    a, b = _both(backends, "pu_bridge_gate", lambda: [F0, 768, 512, E, 512, 256, B * J, *_pair(B * J, 512)])
+    _same(a[7].float() + a[8].float(), b[7].float() + b[8].float(), 2e-5)
+    src = torch.randn(40, 72)
+    a, b = _both(backends, "split2d", lambda: [src, 40, 64, 72, *_pair(40, 128), 128])
+    _same(a[4], b[4]); _same(a[5], b[5])
+    v1, v2, v3 = torch.randn(100), torch.randn(100), torch.randn(100)
+    a, b = _both(backends, "add3", lambda: [v1, v2, v3, torch.zeros(100), 100])
+    _same(a[3], b[3], 1e-6)
