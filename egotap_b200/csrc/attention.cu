@@ -18,6 +18,7 @@
 
 namespace eb {
 
+#ifndef EB_HOST_EMU      // (the CUDA-on-CPU emulation of the tests provides functional models of these four)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -48,6 +49,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+#endif
 
 // Debug-only wait-cycle accounting (tools/attn_trace.sh builds a separate library with -DEB_ATTN_TRACE).
 #ifdef EB_ATTN_TRACE
@@ -100,7 +103,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
                  const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                  __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items, int qtiles) {
   using C = AttnCfg<NSPLIT>;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint8_t* sQ = smem;
   uint8_t* sRing = smem + C::Q_BYTES;
@@ -272,7 +275,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
 #ifdef EB_ATTN_TRACE
     const long long tr_start_ = clock64();
 #endif
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    auto pair_sync = [&]() { named_bar_sync<64>(1 + q); };
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const uint32_t t_o = C::T_O + (it & 1) * AT_D;
       float m_ref = 0.f, l = 0.f;
@@ -405,13 +408,13 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
   if (!attr_done[dev_]) {
-    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EB_CUDA(EB_SET_MAX_SMEM(kern, C::SMEM_BYTES));
     attr_done[dev_] = true;
   }
   const int items = B * AT_HEADS * qtiles;
   const int grid = items < num_sms() ? items : num_sms();
   ProfScope prof("attention_kernel", stream);
-  kern<<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ctx_hi, ctx_lo, items, qtiles);
+  EB_LAUNCH_SMEM(kern, grid, AT_THREADS, C::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], ctx_hi, ctx_lo, items, qtiles);
   EB_CHECK_LAUNCH("attention_kernel");
   return 0;
 }

@@ -181,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
   using C = GemmCfg<CG, BN, NSPLIT, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
+  EB_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
   uint64_t* empty = full + STAGES;

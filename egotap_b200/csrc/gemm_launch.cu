@@ -15,7 +15,7 @@ static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiPa
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
   if (!attr_done[dev_]) {
-    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EB_CUDA(EB_SET_MAX_SMEM(kern, C::SMEM_BYTES));
     attr_done[dev_] = true;
   }
   const int nM = (s.M + C::BM * CG - 1) / (C::BM * CG);
@@ -23,20 +23,8 @@ static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiPa
   const long long tiles = (long long)s.groups * nM * nN;
   long long nclusters = num_sms() / CG;
   if (tiles < nclusters) nclusters = tiles;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(nclusters * CG));
-  cfg.blockDim = dim3(C::THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  EB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], s, ep));
+  EB_CUDA(EB_LAUNCH_CLUSTER(kern, (unsigned)(nclusters * CG), C::THREADS, C::SMEM_BYTES, CG, stream, tm[0], tm[1], tm[2], tm[3],
+                            s, ep));
   EB_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }

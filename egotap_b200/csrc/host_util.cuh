@@ -49,6 +49,21 @@ inline std::atomic<long long>& launch_counter() {
 // shared-memory atomics); EB_LAUNCH kernels have fully independent threads.  Both are the plain <<<>>> launch here --
 // the distinction only matters to the CUDA-on-CPU emulation the tests build with -DEB_HOST_EMU (tests/cuda_emu), which
 // runs independent-thread kernels as a loop and cooperative ones on fibers.
+// EB_LAUNCH_CLUSTER: kernels with dynamic shared memory and (optionally) a thread-block cluster; EB_SET_MAX_SMEM: the
+// per-device opt-in to > 48 KB of dynamic shared memory
+#ifdef EB_HOST_EMU
+#define EB_SET_MAX_SMEM(kernel, bytes) cudaSuccess
+#define EB_LAUNCH_CLUSTER(kernel, grid, block, smem, cluster, stream, ...) \
+  (eb_emu::launch_ex(dim3(grid), dim3(block), (cluster), (smem), [=]() { kernel(__VA_ARGS__); }), cudaSuccess)
+#define EB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+  eb_emu::launch_ex(dim3(grid), dim3(block), 1, (smem), [=]() { kernel(__VA_ARGS__); })
+#else
+#define EB_SET_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+#define EB_LAUNCH_CLUSTER(kernel, grid, block, smem, cluster, stream, ...) \
+  eb::launch_cluster(kernel, grid, block, smem, cluster, stream, __VA_ARGS__)
+#define EB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 #ifdef EB_HOST_EMU
 #define EB_LAUNCH(kernel, grid, block, stream, ...) \
   eb_emu::launch(dim3(grid), dim3(block), false, [=]() { kernel(__VA_ARGS__); })
@@ -114,6 +129,12 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+#ifdef EB_HOST_EMU
+// emulation: the same arguments and checks, recorded in the opaque CUtensorMap storage for tests/cuda_emu/ptx_emu.h
+inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, long long rows, long long ld,
+                             long long g0_count, long long g0_stride, long long g1_count, long long g1_stride,
+                             int box_rows);
+#else
 // 4-D bf16 tensor map [g1][g0][rows][K] (K contiguous), box = 64 x box_rows x 1 x 1, 128-byte swizzle.
 inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, long long rows, long long ld,
                              long long g0_count, long long g0_stride, long long g1_count, long long g1_stride,
@@ -139,6 +160,12 @@ inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, lon
   return 0;
 }
 
+#endif  // EB_HOST_EMU (make_operand_tmap)
+
+#ifdef EB_HOST_EMU
+inline int current_device() { return 0; }
+inline int num_sms() { return eb_emu::num_sms(); }
+#else
 inline int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -151,5 +178,54 @@ inline int num_sms() {
   if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
   return n[dev];
 }
+#endif
+
+#ifndef EB_HOST_EMU
+// cudaLaunchKernelEx with a cluster dimension attribute (cluster = 1: a plain launch with dynamic shared memory)
+template <class Kernel, class... Args>
+inline cudaError_t launch_cluster(Kernel kernel, unsigned grid, unsigned block, size_t smem, int cluster, cudaStream_t stream,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
 
 }  // namespace eb
+
+#ifdef EB_HOST_EMU
+#include "ptx_emu.h"
+namespace eb {
+inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, long long rows, long long ld,
+                             long long g0_count, long long g0_stride, long long g1_count, long long g1_stride,
+                             int box_rows) {
+  if (g0_count < 1) g0_count = 1;
+  if (g1_count < 1) g1_count = 1;
+  if (g0_stride <= 0) g0_stride = rows * ld;
+  if (g1_stride <= 0) g1_stride = g0_stride * g0_count;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15) || ((g0_stride * 2) & 15) || ((g1_stride * 2) & 15))
+    return fail(EGOTAP_E_ARG, "TMA operand must be 16-byte aligned (base %p ld %lld)", base, ld);
+  if (K < 1 || rows < 1 || box_rows < 1 || box_rows > 256)
+    return fail(EGOTAP_E_DRIVER, "cuTensorMapEncodeTiled (emulated) failed: K %lld rows %lld ld %lld box %d", K, rows, ld, box_rows);
+  memset(tm, 0, sizeof(*tm));
+  EmuTmap* e = reinterpret_cast<EmuTmap*>(tm);
+  e->base = static_cast<const uint8_t*>(base);
+  e->dims[0] = uint64_t(K); e->dims[1] = uint64_t(rows); e->dims[2] = uint64_t(g0_count); e->dims[3] = uint64_t(g1_count);
+  e->strides[0] = uint64_t(ld) * 2; e->strides[1] = uint64_t(g0_stride) * 2; e->strides[2] = uint64_t(g1_stride) * 2;
+  e->box_rows = uint32_t(box_rows);
+  e->magic = 0x7e4a0001u;
+  return 0;
+}
+}  // namespace eb
+#endif

@@ -2,6 +2,10 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM alloc / ld / commit), clusters.
 // Encodings follow the PTX ISA 8.7 (CUDA 12.9) tcgen05 chapter.
 #pragma once
+#ifdef EB_HOST_EMU          // CUDA-on-CPU emulation of the tests (tests/cuda_emu): functional model of these wrappers
+#include "ptx_emu.h"
+#include "numeric.cuh"
+#else
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -9,6 +13,10 @@
 #include <cstdio>
 
 #include "numeric.cuh"
+
+// dynamic shared memory of the kernel (the emulation substitutes a per-CTA host buffer)
+#define EB_DYN_SMEM(name) extern __shared__ uint8_t name[]
+#define EB_DYN_SMEM_1K(name) extern __shared__ __align__(1024) uint8_t name[]
 
 namespace eb {
 
@@ -38,6 +46,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
   return r;
+}
+// named barrier among N threads of the CTA (bar.sync id, N)
+template <int N>
+__device__ __forceinline__ void named_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -228,3 +241,4 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace eb
+#endif  // EB_HOST_EMU

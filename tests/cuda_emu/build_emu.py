@@ -9,7 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "egotap_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
-SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "train_ops.cu"),
+SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(HERE, "selftest.cu"), os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "gemm_launch.cu"),
+           os.path.join(CSRC, "attention.cu"),
+           os.path.join(CSRC, "train_ops.cu"),
            os.path.join(CSRC, "train_model.cu"),
            os.path.join(CSRC, "gt_heatmap.cu")]
 CUDA_INC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -17,7 +19,8 @@ CUDA_LIB = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
 
 
 def build(force=False):
-    deps = SOURCES + [os.path.join(HERE, "cuda_emu.h"), os.path.join(CSRC, "host_util.cuh"), os.path.join(CSRC, "numeric.cuh"),
+    deps = SOURCES + [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "ptx_emu.h"), os.path.join(CSRC, "host_util.cuh"),
+                      os.path.join(CSRC, "numeric.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "gemm.cuh"),
                       os.path.join(ROOT, "include", "egotap_b200.h")]
     if not force and os.path.isfile(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
@@ -25,7 +28,7 @@ def build(force=False):
     # -fsanitize=alignment: every pointer dereference is checked against its type's alignment (float4 / uint4: 16 bytes,
     # float2 / uint2: 8, packed bf16x2 stores: 4) and aborts on a violation -- the one class of kernel bug that plain x86
     # execution would forgive and the GPU would not
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DEB_HOST_EMU", "-fsanitize=alignment",
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O3", "-mavx2", "-fno-strict-aliasing", "-fPIC", "-shared", "-DEB_HOST_EMU", "-fsanitize=alignment",
            "-fno-sanitize-recover=alignment", "-I", HERE, "-I", CUDA_INC, "-I", CSRC, "-o", OUT] + SOURCES + \
           ["-L", CUDA_LIB, "-Wl,-rpath," + CUDA_LIB, "-lcudart"]     # error-string / event symbols only; no device is touched
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -35,7 +38,7 @@ def build(force=False):
     return OUT
 
 
-def make_backend():
+def make_backend(real_tensor_core=False):
     """A backend for training.TrainEngine whose bandwidth-bound ops -- the training kernels and the round-1 kernels of
     csrc/kernels.cu (ingest, LayerNorm, head, packing) -- execute the real kernel source on the CPU emulation; the
     tensor-core kernels (tcgen05 GEMM, fused attention: GPU-verified in round 1, not emulatable) are served by the op
@@ -51,6 +54,9 @@ def make_backend():
     for name, args in capi._TRAIN_ARGTYPES(C.c_void_p, C.c_longlong, C.c_int, C.c_float).items():
         getattr(lib, name).argtypes = args
     P, I = C.c_void_p, C.c_int
+    lib.egotap_b200_gemm.argtypes = [C.POINTER(capi.Gemm), C.c_void_p]
+    lib.egotap_b200_gemm_variant_name.restype = C.c_char_p
+    lib.egotap_b200_attention.argtypes = [P] * 6 + [I, I, P]
     lib.egotap_b200_ingest.argtypes = [P, I, I] + [P] * 5
     lib.egotap_b200_layernorm.argtypes = [P] * 3 + [C.c_longlong, I, I, C.c_float] + [P] * 4
     lib.egotap_b200_head.argtypes = [P, I] + [P] * 5 + [C.c_longlong, I, P, P]
@@ -86,8 +92,33 @@ def make_backend():
 
         # the tensor-core kernels cannot be emulated: oracle.  Everything else (round-1 bandwidth kernels of
         # csrc/kernels.cu included) runs the real kernel source through the inherited CudaBackend methods.
-        def gemm(self, *a, **k): self._py(orc.gemm, *a, **k)
-        def attention(self, *a): self._py(orc.attention, *a)
+        def gemm(self, *a, **k):
+            if real_tensor_core:
+                self.gemm_tc(*a, **k)
+            else:
+                self._py(orc.gemm, *a, **k)
+
+        def attention(self, *a):
+            if real_tensor_core:
+                self.attention_tc(*a)
+            else:
+                self._py(orc.attention, *a)
+
+        # ... but their SOURCE does run on the functional tcgen05 / TMA / mbarrier model (ptx_emu.h), for op-level tests
+        def gemm_tc(self, *a, **k):
+            saved, capi.require_cuda = capi.require_cuda, (lambda *t: None)
+            try:
+                d = capi.gemm_desc(*a, **k)
+            finally:
+                capi.require_cuda = saved
+            self._c("egotap_b200_gemm", C.byref(d), None)
+
+        def attention_tc(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, frames, precision):
+            p = lambda t: None if t is None else t.data_ptr()
+            self._c("egotap_b200_attention", p(qk_hi), p(qk_lo), p(vt_hi), p(vt_lo), p(ctx_hi), p(ctx_lo), frames, precision, None)
+
+        def gemm_variant_names(self):
+            return [lib.egotap_b200_gemm_variant_name(i).decode() for i in range(lib.egotap_b200_gemm_num_variants())]
 
     return EmuBackend(), orc
 

@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- runtime of the CUDA-on-CPU emulation (see cuda_emu.h) plus the few symbols the emulated
-// translation units expect from the rest of libegotap_b200.so.
+// translation units expect from the parts of libegotap_b200.so that are not emulated.
 #include "cuda_emu.h"
 
 #include <ucontext.h>
@@ -13,25 +13,45 @@ uint3 g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 
 namespace {
-constexpr size_t kStack = 256 * 1024;
+constexpr size_t kStack = 512 * 1024;
+constexpr int kMaxWarps = 64, kNamed = 16;
 struct Fiber {
   ucontext_t ctx;
   std::vector<char> stack;
   bool done = false;
-  int warp = 0, lane = 0;
+  int cta = 0, warp = 0, lane = 0, tid = 0;
+  // what a blocked fiber waits for, so the scheduler does not switch to it in vain: a barrier generation counter that
+  // must move on, or an mbarrier phase bit (top bit of its first 16-bit word) that must differ from `parity`
+  const unsigned* wait_gen = nullptr;
+  unsigned wait_val = 0;
+  const uint16_t* wait_phase = nullptr;
+  unsigned wait_parity = 0;
+};
+struct Cta {
+  std::vector<uint8_t> smem_store;
+  uint8_t* smem = nullptr;
+  std::vector<uint32_t> tmem;
+  uint32_t tmem_next = 0;
+  uint3 block_idx;
+  int live = 0, block_waiting = 0;
+  unsigned block_gen = 0;
+  int warp_live[kMaxWarps], warp_waiting[kMaxWarps];
+  unsigned warp_gen[kMaxWarps];
+  float warp_buf[kMaxWarps][32];
+  int named_waiting[kNamed], named_need[kNamed];
+  unsigned named_gen[kNamed];
 };
 std::vector<Fiber> fibers;
+std::vector<Cta> ctas;
 ucontext_t sched_ctx;
 Fiber* cur = nullptr;
 bool in_coop = false;
 const std::function<void()>* cur_body = nullptr;
-// barrier state of the running CTA
-int live = 0, block_waiting = 0;
-unsigned block_gen = 0;
-int warp_live[64], warp_waiting[64];
-unsigned warp_gen[64];
-float warp_buf[64][32];
+int cluster_live = 0, cluster_waiting = 0;
+unsigned cluster_gen = 0;
+unsigned long long progress = 0;
 
+Cta& C() { return ctas[cur->cta]; }
 void yield() { swapcontext(&cur->ctx, &sched_ctx); }
 
 void trampoline() {
@@ -41,91 +61,203 @@ void trampoline() {
 }
 
 void release_ready_barriers() {
-  if (block_waiting > 0 && block_waiting == live) { block_waiting = 0; ++block_gen; }
-  for (int w = 0; w < 64; ++w)
-    if (warp_waiting[w] > 0 && warp_waiting[w] == warp_live[w]) { warp_waiting[w] = 0; ++warp_gen[w]; }
+  for (Cta& c : ctas) {
+    if (c.block_waiting > 0 && c.block_waiting == c.live) { c.block_waiting = 0; ++c.block_gen; ++progress; }
+    for (int w = 0; w < kMaxWarps; ++w)
+      if (c.warp_waiting[w] > 0 && c.warp_waiting[w] == c.warp_live[w]) { c.warp_waiting[w] = 0; ++c.warp_gen[w]; ++progress; }
+    for (int i = 0; i < kNamed; ++i)
+      if (c.named_waiting[i] > 0 && c.named_waiting[i] >= c.named_need[i]) { c.named_waiting[i] = 0; ++c.named_gen[i]; ++progress; }
+  }
+  if (cluster_waiting > 0 && cluster_waiting == cluster_live) { cluster_waiting = 0; ++cluster_gen; ++progress; }
+}
+
+void need_coop(const char* what) {
+  if (!in_coop) { fprintf(stderr, "cuda_emu: %s in a kernel launched with EB_LAUNCH\n", what); abort(); }
+}
+
+void wait_gen(const unsigned* gen, unsigned val) {
+  while (*gen == val) {
+    cur->wait_gen = gen;
+    cur->wait_val = val;
+    yield();
+  }
 }
 
 void warp_barrier() {
+  Cta& c = C();
   const int w = cur->warp;
-  const unsigned gen = warp_gen[w];
-  ++warp_waiting[w];
-  while (warp_gen[w] == gen) yield();
+  const unsigned gen = c.warp_gen[w];
+  ++c.warp_waiting[w];
+  wait_gen(&c.warp_gen[w], gen);
 }
 }  // namespace
 
+void note_progress() { ++progress; }
+void yield_wait() { need_coop("a spinning wait"); yield(); }
+void wait_phase(const void* mbar_word, unsigned parity) {
+  need_coop("an mbarrier wait");
+  const uint16_t* w = static_cast<const uint16_t*>(mbar_word);
+  while (unsigned((*w >> 15) & 1) == (parity & 1)) {
+    cur->wait_phase = w;
+    cur->wait_parity = parity & 1;
+    yield();
+  }
+}
+uint8_t* dyn_smem() { return C().smem; }
+uint8_t* smem_of(int r) { return ctas[r].smem; }
+uint32_t* tmem_of(int r) { return ctas[r].tmem.data(); }
+uint32_t& tmem_next_col() { return C().tmem_next; }
+int cta_rank() { return cur ? cur->cta : 0; }
+int lane() { return cur ? cur->lane : 0; }
+int num_sms() { return 6; }     // a small "device": persistent kernels then loop over several tiles per CTA
+
 void syncthreads() {
-  if (!in_coop) { fprintf(stderr, "cuda_emu: __syncthreads() in a kernel launched with EB_LAUNCH\n"); abort(); }
-  const unsigned gen = block_gen;
-  ++block_waiting;
-  while (block_gen == gen) yield();
+  need_coop("__syncthreads()");
+  Cta& c = C();
+  const unsigned gen = c.block_gen;
+  ++c.block_waiting;
+  wait_gen(&c.block_gen, gen);
+}
+void syncwarp() { need_coop("__syncwarp()"); warp_barrier(); }
+void named_barrier(int id, int nthreads) {
+  need_coop("bar.sync");
+  Cta& c = C();
+  if (id < 0 || id >= kNamed) { fprintf(stderr, "cuda_emu: named barrier id %d\n", id); abort(); }
+  const unsigned gen = c.named_gen[id];
+  c.named_need[id] = nthreads;
+  ++c.named_waiting[id];
+  wait_gen(&c.named_gen[id], gen);
+}
+void cluster_sync() {
+  need_coop("cluster barrier");
+  const unsigned gen = cluster_gen;
+  ++cluster_waiting;
+  wait_gen(&cluster_gen, gen);
 }
 
 float shfl_xor(float v, int lane_mask) {
-  if (!in_coop) { fprintf(stderr, "cuda_emu: warp shuffle in a kernel launched with EB_LAUNCH\n"); abort(); }
-  warp_buf[cur->warp][cur->lane] = v;
+  need_coop("warp shuffle");
+  Cta& c = C();
+  c.warp_buf[cur->warp][cur->lane] = v;
   warp_barrier();
-  const float r = warp_buf[cur->warp][cur->lane ^ lane_mask];
+  const float r = c.warp_buf[cur->warp][cur->lane ^ lane_mask];
+  warp_barrier();
+  return r;
+}
+
+bool any_sync(bool pred) {
+  need_coop("warp vote");
+  Cta& c = C();
+  c.warp_buf[cur->warp][cur->lane] = pred ? 1.f : 0.f;
+  warp_barrier();
+  bool r = false;
+  for (int i = 0; i < 32; ++i) r = r || c.warp_buf[cur->warp][i] != 0.f;   // (all kernels here use full warps)
   warp_barrier();
   return r;
 }
 
 void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>& body) {
+  if (cooperative) { launch_ex(grid, block, 1, 0, body); return; }
   g_blockDim = block;
   g_gridDim = grid;
+  in_coop = false;
+  cur = nullptr;
   const int nthreads = int(block.x * block.y * block.z);
-  if (block.y != 1 || block.z != 1 || nthreads > 2048) { fprintf(stderr, "cuda_emu: unsupported block shape\n"); abort(); }
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_blockIdx = make_uint3(bx, by, bz);
-        if (!cooperative) {
-          in_coop = false;
-          for (int t = 0; t < nthreads; ++t) {
-            g_threadIdx = make_uint3(unsigned(t), 0, 0);
-            body();
-          }
-          continue;
-        }
-        in_coop = true;
-        cur_body = &body;
-        if (int(fibers.size()) < nthreads) fibers.resize(nthreads);
-        live = nthreads;
-        block_waiting = 0;
-        for (int w = 0; w < 64; ++w) { warp_live[w] = 0; warp_waiting[w] = 0; }
         for (int t = 0; t < nthreads; ++t) {
-          Fiber& f = fibers[t];
-          if (f.stack.empty()) f.stack.resize(kStack);
-          f.done = false;
-          f.warp = t / 32;
-          f.lane = t % 32;
-          ++warp_live[f.warp];
-          getcontext(&f.ctx);
-          f.ctx.uc_stack.ss_sp = f.stack.data();
-          f.ctx.uc_stack.ss_size = f.stack.size();
-          f.ctx.uc_link = &sched_ctx;
-          makecontext(&f.ctx, trampoline, 0);
+          g_threadIdx = make_uint3(unsigned(t), 0, 0);
+          body();
         }
-        long spins = 0;
-        while (live > 0) {
-          bool progressed = false;
-          for (int t = 0; t < nthreads; ++t) {
-            Fiber& f = fibers[t];
-            if (f.done) continue;
-            cur = &f;
-            g_threadIdx = make_uint3(unsigned(t), 0, 0);
-            const unsigned bg = block_gen, wg = warp_gen[f.warp];
-            const int bw = block_waiting, ww = warp_waiting[f.warp];
-            swapcontext(&sched_ctx, &f.ctx);
-            if (f.done) { --live; --warp_live[f.warp]; progressed = true; }
-            if (bg != block_gen || wg != warp_gen[f.warp] || bw != block_waiting || ww != warp_waiting[f.warp]) progressed = true;
-            release_ready_barriers();
-          }
-          if (!progressed && ++spins > 4) { fprintf(stderr, "cuda_emu: deadlock (divergent barrier?)\n"); abort(); }
-          if (progressed) spins = 0;
-        }
-        in_coop = false;
       }
+}
+
+void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const std::function<void()>& body) {
+  g_blockDim = block;
+  g_gridDim = grid;
+  const int nthreads = int(block.x * block.y * block.z);
+  if (block.y != 1 || block.z != 1 || nthreads > 2048 || cluster < 1 || (cluster > 1 && (grid.y != 1 || grid.z != 1 || grid.x % cluster))) {
+    fprintf(stderr, "cuda_emu: unsupported launch shape\n");
+    abort();
+  }
+  const long long nblocks = (long long)grid.x * grid.y * grid.z;
+  ctas.resize(cluster);
+  for (Cta& c : ctas) {
+    c.smem_store.assign(dyn_smem_bytes + 2048, 0xCD);                      // poisoned: uninitialised reads stand out
+    c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(c.smem_store.data()) + 1023) & ~uintptr_t(1023));
+    c.tmem.assign(128 * 512, 0x7fc00000u);                                 // NaN-filled tensor memory
+  }
+  if (int(fibers.size()) < cluster * nthreads) fibers.resize(cluster * nthreads);
+  in_coop = true;
+  cur_body = &body;
+  for (long long b0 = 0; b0 < nblocks; b0 += cluster) {
+    cluster_live = cluster * nthreads;
+    cluster_waiting = 0;
+    for (int k = 0; k < cluster; ++k) {
+      Cta& c = ctas[k];
+      const long long b = b0 + k;
+      c.block_idx = make_uint3(unsigned(b % grid.x), unsigned((b / grid.x) % grid.y), unsigned(b / ((long long)grid.x * grid.y)));
+      c.live = nthreads;
+      c.block_waiting = 0;
+      c.tmem_next = 0;
+      for (int w = 0; w < kMaxWarps; ++w) { c.warp_live[w] = 0; c.warp_waiting[w] = 0; }
+      for (int i = 0; i < kNamed; ++i) { c.named_waiting[i] = 0; c.named_need[i] = 1 << 30; }
+      for (int t = 0; t < nthreads; ++t) {
+        Fiber& f = fibers[k * nthreads + t];
+        if (f.stack.empty()) f.stack.resize(kStack);
+        f.done = false;
+        f.wait_gen = nullptr; f.wait_phase = nullptr;
+        f.cta = k; f.tid = t; f.warp = t / 32; f.lane = t % 32;
+        ++c.warp_live[f.warp];
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_link = &sched_ctx;
+        makecontext(&f.ctx, trampoline, 0);
+      }
+    }
+    int idle_rounds = 0;
+    while (cluster_live > 0) {
+      const unsigned long long before = progress;
+      for (int i = 0; i < cluster * nthreads; ++i) {
+        Fiber& f = fibers[i];
+        if (f.done) continue;
+        if (f.wait_gen) {
+          if (*f.wait_gen == f.wait_val) continue;
+          f.wait_gen = nullptr;
+        }
+        if (f.wait_phase) {
+          if (unsigned((*f.wait_phase >> 15) & 1) == f.wait_parity) continue;
+          f.wait_phase = nullptr;
+        }
+        cur = &f;
+        g_threadIdx = make_uint3(unsigned(f.tid), 0, 0);
+        g_blockIdx = ctas[f.cta].block_idx;
+        swapcontext(&sched_ctx, &f.ctx);
+        if (f.done) {
+          --cluster_live; --ctas[f.cta].live; --ctas[f.cta].warp_live[f.warp]; ++progress;
+        }
+        release_ready_barriers();
+      }
+      if (progress == before) {
+        if (++idle_rounds > 3) {
+          fprintf(stderr, "cuda_emu: DEADLOCK -- every live thread of the cluster is waiting (block %u); waiting threads:",
+                  ctas[0].block_idx.x);
+          int shown = 0;
+          for (int i = 0; i < cluster * nthreads && shown < 16; ++i)
+            if (!fibers[i].done) { fprintf(stderr, " cta%d/t%d", fibers[i].cta, fibers[i].tid); ++shown; }
+          fprintf(stderr, "\n");
+          abort();
+        }
+      } else {
+        idle_rounds = 0;
+      }
+    }
+  }
+  in_coop = false;
+  cur = nullptr;
 }
 
 }  // namespace eb_emu
@@ -135,7 +267,7 @@ void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>
 namespace eb {
 bool& prof_on() { static bool off = false; return off; }
 void prof_push(const ProfRec&) {}
-// declared locally in plan.cu (which holds the tensor-core plan and cannot be emulated)
+// declared locally in plan.cu (which holds the whole-path plan and is not emulated)
 int ingest_run(const float*, int, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
 int layernorm_run(const float*, const float*, const float*, long long, int, int, float, __nv_bfloat16*, __nv_bfloat16*,
                   float*, cudaStream_t);

@@ -1,28 +1,52 @@
-// TEST INFRASTRUCTURE ONLY -- a minimal CUDA-on-CPU execution model, so that the SOURCE of the bandwidth-bound
-// training kernels (egotap_b200/csrc/train_ops.cu, train_model.cu) can be compiled by g++ (-DEB_HOST_EMU) and run in
-// the GPU-less build container against the op oracle.  It checks indexing, layouts, reductions and arithmetic of the
-// kernel code itself; it says nothing about performance, memory coalescing or hardware-specific behaviour, and the
-// tensor-core kernels (tcgen05 / TMA / mbarrier) are out of its reach -- those were verified on the B200 in round 1.
+// TEST INFRASTRUCTURE ONLY -- a minimal CUDA-on-CPU execution model, so that the SOURCE of the product's kernels can be
+// compiled by g++ (-DEB_HOST_EMU) and run in the GPU-less build container against the op oracle.
 //
-// Execution model: CTAs run one after another.  Kernels launched with EB_LAUNCH have independent threads and run as a
-// plain loop; EB_LAUNCH_COOP kernels run every thread of the CTA as a fiber (ucontext) so __syncthreads() and
-// __shfl_xor_sync() have their real meaning (threads that return early drop out of the barriers, as on the GPU).
-// __shared__ variables become function-local statics (one CTA at a time, one OS thread).
+//   * bandwidth-bound kernels (csrc/kernels.cu, train_ops.cu, train_model.cu, gt_heatmap.cu): exact execution of the
+//     kernel code -- indexing, layouts, reductions, arithmetic, alignment (-fsanitize=alignment)
+//   * tensor-core kernels (csrc/gemm.cuh, attention.cu): a FUNCTIONAL model of the sm_100a features they use -- mbarrier
+//     (arrival counts, transaction bytes, phase parity), TMA tiled loads with the 128-byte swizzle and zero fill,
+//     tensor memory, tcgen05.mma (SS and TS forms, cta_group 1 and 2) decoding the real shared-memory / instruction
+//     descriptors, tcgen05.ld / st, clusters -- see ptx_emu.h.  It checks protocol (no deadlock, every wait satisfied),
+//     addressing and arithmetic of the kernel code; asynchronous operations complete immediately, so it cannot see a
+//     MISSING wait, and it says nothing about speed.  The model was calibrated on kernels verified on the B200.
+//
+// Execution model: thread-block clusters run one after another; every thread of a cooperative launch is a fiber
+// (ucontext), so __syncthreads(), named barriers, warp shuffles, __syncwarp() and mbarrier waits have their real meaning
+// (threads that return early drop out of the barriers).  EB_LAUNCH kernels (independent threads) run as a plain loop.
+// Static __shared__ variables become function-local statics (valid because such kernels run one CTA at a time);
+// dynamic shared memory is a per-CTA 1024-byte aligned buffer.
 #pragma once
+#include <cuda.h>           // CUtensorMap (opaque 128-byte storage)
 #include <cuda_runtime.h>   // host-side vector types, dim3, cudaStream_t, error codes
+#include <cuda_bf16.h>      // __nv_bfloat16 (2-byte storage type; host-compilable)
 #include <stdint.h>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
-
-#include <cuda_bf16.h>   // __nv_bfloat16 (2-byte storage type; host-compilable)
 
 namespace eb_emu {
 extern uint3 g_threadIdx, g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>& body);
+void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem, const std::function<void()>& body);
 void syncthreads();
+void syncwarp();
+void named_barrier(int id, int nthreads);
+void cluster_sync();
 float shfl_xor(float v, int lane_mask);
+bool any_sync(bool pred);
+void wait_phase(const void* mbar_first_word, unsigned parity);   // block until the mbarrier phase bit != parity
+void yield_wait();              // a spinning wait gives the other fibers a turn (and feeds the deadlock detector)
+void note_progress();           // any state change another fiber may be waiting for
+uint8_t* dyn_smem();            // dynamic shared memory of the running CTA
+uint8_t* smem_of(int cta_rank); // ... of a CTA of the running cluster
+uint32_t* tmem_of(int cta_rank);// tensor memory (128 lanes x 512 columns of 32 bits) of a CTA of the running cluster
+uint32_t& tmem_next_col();      // allocation cursor of the running CTA
+int cta_rank();
+int lane();
+int num_sms();
 }  // namespace eb_emu
 
 #define threadIdx eb_emu::g_threadIdx
@@ -33,11 +57,17 @@ float shfl_xor(float v, int lane_mask);
 #define __shared__ static
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#undef __grid_constant__
+#define __grid_constant__
 #define __syncthreads() eb_emu::syncthreads()
+#define __syncwarp() eb_emu::syncwarp()
 #define __shfl_xor_sync(mask, v, o) eb_emu::shfl_xor((v), (o))
+#define __any_sync(mask, p) eb_emu::any_sync(p)
+#define __trap() (fprintf(stderr, "cuda_emu: __trap() at %s:%d\n", __FILE__, __LINE__), abort())
 #define __ldg(p) (*(p))
 #define __expf(x) expf(x)
 inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
 #define cudaMemcpyAsync(d, s, n, kind, st) (memcpy((d), (s), (n)), cudaSuccess)

@@ -1,0 +1,39 @@
+// TEST INFRASTRUCTURE ONLY -- self-test kernels of the emulation (compiled into the emulation library only): a
+// producer / consumer hand-off through two mbarriers written with the product's own wrappers (ptx.cuh names).  The
+// correct protocol must run; the broken one (consumer waits on the wrong phase parity once) must be reported as a
+// deadlock by the fiber scheduler instead of hanging or silently passing.
+#include "ptx.cuh"
+
+namespace {
+void handoff_kernel(int rounds, int break_at, int* out) {
+  using namespace eb;
+  EB_DYN_SMEM(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 1;
+  int* slot = reinterpret_cast<int*>(smem + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(full, 1); mbar_init(empty, 1); fence_mbar_init(); }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0)
+      for (int i = 0; i < rounds; ++i) {
+        mbar_wait(empty, (i & 1) ^ 1);
+        *slot = 100 + i;
+        mbar_arrive(full);
+      }
+  } else if (lane == 0) {
+    int sum = 0;
+    for (int i = 0; i < rounds; ++i) {
+      mbar_wait(full, (i == break_at) ? ((i & 1) ^ 1) : (i & 1));   // break_at >= 0: one wait on the wrong parity
+      sum += *slot;
+      mbar_arrive(empty);
+    }
+    *out = sum;
+  }
+}
+}  // namespace
+
+extern "C" int emu_selftest_handoff(int rounds, int break_at, int* out) {
+  eb_emu::launch_ex(dim3(1), dim3(64), 1, 1024, [=]() { handoff_kernel(rounds, break_at, out); });
+  return 0;
+}

@@ -1,0 +1,243 @@
+"""The SOURCE of the tensor-core kernels -- the persistent tcgen05 GEMM (csrc/gemm.cuh, all six tile configurations) and
+the fused attention kernel (csrc/attention.cu) -- compiled by g++ against a FUNCTIONAL model of the sm_100a features they
+use (tests/cuda_emu/ptx_emu.h: mbarrier counts / transaction bytes / phase parity, TMA tiled loads with the 128-byte
+swizzle and zero fill, tensor memory, tcgen05.mma SS and TS forms decoding the real matrix / instruction descriptors,
+cta_group::2 pairs, tcgen05.ld / st, named barriers; every thread a fiber, deadlocks detected) and compared with the op
+oracle.  Both kernels were verified on the B200 in round 1, so these tests (a) calibrate the model, (b) keep the kernels'
+addressing / protocol under regression test without a GPU, and (c) let restructured kernels be brought up offline before
+they spend GPU time.  The model completes asynchronous operations at issue: it cannot detect a MISSING wait, and it
+says nothing about speed."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import op_oracle
+import train_oracle as tro
+import weights
+from egotap_b200 import training
+from egotap_b200.synthetic import synthetic_heatmaps
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cuda_emu"))
+import build_emu  # noqa: E402
+
+BF16 = torch.bfloat16
+VARIANTS = [(0, 1), (1, 0), (2, 1), (3, 0), (4, 1), (5, 0)]      # (tile configuration, precision: 0 = bf16x3, 1 = bf16)
+
+
+@pytest.fixture(scope="module")
+def be():
+    return build_emu.make_backend()
+
+
+def _pairs(x):
+    return op_oracle.split(x)
+
+
+def _run_both(be, a, b, M, N, K, prec, variant, make_epi, **kw):
+    """the same GEMM on the emulated kernel and on the oracle; make_epi() builds fresh (poisoned) outputs"""
+    emu, orc = be
+    ah, al = _pairs(a)
+    bh, bl = _pairs(b)
+    if prec == 1:
+        al = bl = None
+    e1, e2 = make_epi(), make_epi()
+    emu.gemm_tc(ah, al, bh, bl, M, N, K, precision=prec, variant=variant, **kw, **e1)
+    orc.gemm(ah, al, bh, bl, M, N, K, precision=prec, **kw, **e2)
+    return e1, e2
+
+
+def _close(x, y, tol):
+    x, y = x.float(), y.float()
+    assert torch.isnan(x).equal(torch.isnan(y)), "never-written (NaN) pattern differs"
+    x, y = torch.nan_to_num(x), torch.nan_to_num(y)
+    assert (x - y).abs().max().item() <= tol * max(y.abs().max().item(), 1e-30), (x - y).abs().max().item()
+
+
+@pytest.mark.parametrize("variant,prec", VARIANTS)
+def test_gemm_tile_configurations(be, variant, prec):
+    """ragged M (TMA zero fill), several tiles per persistent CTA, bias + GELU, fp32 and bf16-pair outputs"""
+    torch.manual_seed(variant)
+    M, N, K = 456, 512, 192
+    a, b = torch.randn(M, K), torch.randn(N, K)
+    bias = torch.randn(N)
+
+    def epi():
+        return dict(bias=bias, act=1, out_f32=torch.full((M, N), float("nan")), out_hi=torch.full((M, N), float("nan"), dtype=BF16),
+                    out_lo=None if prec else torch.full((M, N), float("nan"), dtype=BF16))
+    e1, e2 = _run_both(be, a, b, M, N, K, prec, variant, epi)
+    tol = 2e-5 if prec == 0 else 1e-6          # bf16x3 drops the lo*lo term (2^-16 relative); plain bf16 is exact products
+    _close(e1["out_f32"], e2["out_f32"], tol)
+    lo1 = 0 if prec else e1["out_lo"].float()
+    lo2 = 0 if prec else e2["out_lo"].float()
+    _close(e1["out_hi"].float() + lo1, e2["out_hi"].float() + lo2, 1e-2 if prec else 1e-4)
+
+
+@pytest.mark.parametrize("variant,prec", [(1, 0), (4, 1), (5, 0)])
+def test_gemm_epilogue_modes(be, variant, prec):
+    torch.manual_seed(10 + variant)
+    tol = 2e-5 if prec == 0 else 1e-6
+    # scale / shift + LeakyReLU, residual table with resid_mod, row re-layout (rows_in -> rows_out), as the patch embedding
+    live, tok, B, N, K = 96, 128, 3, 256, 128
+    M = B * live
+    a, b = torch.randn(M, K), torch.randn(N, K)
+    scale, bias, table = torch.rand(N) + 0.5, torch.randn(N), torch.randn(live, N)
+    e1, e2 = _run_both(be, a, b, M, N, K, prec, variant,
+                       lambda: dict(scale=scale, bias=bias, act=2, resid=table, resid_ld=N, resid_mod=live, rows_in=live, rows_out=tok,
+                                    out_f32=torch.full((B * tok, N), float("nan")), ldo=N))
+    _close(e1["out_f32"], e2["out_f32"], tol)
+    # in-place residual stream (resid == out), as the output projection
+    M = 300
+    a = torch.randn(M, K)
+    h0 = torch.randn(M, N)
+    hs = [h0.clone(), h0.clone()]
+    it = iter(hs)
+
+    def inplace():
+        h = next(it)
+        return dict(bias=bias, resid=h, resid_ld=N, out_f32=h, ldo=N)
+    e1, e2 = _run_both(be, a, b, M, N, K, prec, variant, inplace)
+    _close(hs[0], hs[1], tol)
+    # QKV store: [Q | K] row-major + V transposed per (frame, head)
+    frames, tokens, heads, hd = 2, 64, 2, 128
+    M, N = frames * tokens, 3 * heads * hd
+    a, b = torch.randn(M, K), torch.randn(N, K)
+
+    def qkv():
+        mk = lambda r, c: torch.full((r, c), float("nan"), dtype=BF16)
+        return dict(store=1, qk_cols=2 * heads * hd, tokens=tokens, out_hi=mk(M, 2 * heads * hd), out_lo=None if prec else mk(M, 2 * heads * hd),
+                    ldo=2 * heads * hd, vt_hi=mk(frames * heads * hd, tokens), vt_lo=None if prec else mk(frames * heads * hd, tokens))
+    e1, e2 = _run_both(be, a, b, M, N, K, prec, variant, qkv)
+    for k in ("out_hi", "vt_hi"):
+        _close(e1[k], e2[k], 1e-2)
+    # per-joint regroup store (FC encoder block 3)
+    J, frames = 15, 4
+    M, N, K2 = frames * 2 * J, 128, 512
+    a, b = torch.randn(M, K2), torch.randn(N, K2)
+    e1, e2 = _run_both(be, a, b, M, N, K2, prec, 1 if prec == 0 else 0,
+                       lambda: dict(store=2, J=J, ldo=512, col_off=256, out_f32=torch.full((frames * J, 512), float("nan"))))
+    _close(e1["out_f32"], e2["out_f32"], tol)
+
+
+@pytest.mark.parametrize("variant,prec", [(1, 0), (0, 1)])
+def test_gemm_grouped_operands(be, variant, prec):
+    """the group layouts the path uses: per-(frame, head) attention-style operands with head-merged output, and the
+    split-K chunking of the weight-gradient GEMMs (groups = chunks of the reduction dimension, partial products)"""
+    torch.manual_seed(20 + variant)
+    tol = 2e-5 if prec == 0 else 1e-6
+    emu, orc = be
+    frames, heads, tok, hd = 2, 2, 128, 128
+    q = torch.randn(frames * tok, 2 * heads * hd)               # [Q | K] per token, as the QKV GEMM writes it
+    qh, ql = _pairs(q)
+    if prec:
+        ql = None
+    grp = (heads, hd, frames, tok * 2 * heads * hd)
+    outs = []
+    for b_ in (emu.gemm_tc, orc.gemm):
+        s = torch.full((frames * heads * tok, tok), float("nan"))
+        kw = dict(groups=frames * heads, a_group=grp, b_group=grp, a_rows=tok, b_rows=tok, lda=2 * heads * hd, ldb=2 * heads * hd,
+                  precision=prec, alpha=0.125, out_f32=s, ldo=tok, group_rows=tok)
+        if b_ is emu.gemm_tc:
+            kw["variant"] = variant
+        b_(qh, ql, qh[:, heads * hd:], None if prec else ql[:, heads * hd:], tok, tok, hd, **kw)
+        outs.append(s)
+    _close(outs[0], outs[1], tol)
+    # head-merge store with a column offset (dQ / dK / dV of the attention backward)
+    pmat = torch.randn(frames * heads * tok, tok)
+    vt = torch.randn(frames * heads * hd, tok)
+    ph, pl = _pairs(pmat)
+    vh, vl = _pairs(vt)
+    outs = []
+    for b_ in (emu.gemm_tc, orc.gemm):
+        o = torch.full((frames * tok, 3 * heads * hd), float("nan"))
+        kw = dict(groups=frames * heads, a_group=(heads, tok * tok, frames, heads * tok * tok),
+                  b_group=(heads, hd * tok, frames, heads * hd * tok), a_rows=tok, b_rows=hd, lda=tok, ldb=tok, precision=prec,
+                  store=3, heads=heads, tokens=tok, out_f32=o, ldo=3 * heads * hd, col_off=heads * hd)
+        if b_ is emu.gemm_tc:
+            kw["variant"] = variant
+        b_(ph, None if prec else pl, vh, None if prec else vl, tok, hd, tok, **kw)
+        outs.append(o)
+    _close(outs[0], outs[1], tol)
+    # split-K: dW[n][k] = sum_r dY^T[n][r] X^T[k][r], r cut into G chunks of `chunk` columns
+    n_out, k_out, rows = 256, 128, 300
+    G, chunk = 3, 128
+    ld = training.pad_ld(rows)
+    dyt, xt = torch.zeros(n_out, ld), torch.zeros(k_out, ld)
+    dyt[:, :rows], xt[:, :rows] = torch.randn(n_out, rows), torch.randn(k_out, rows)
+    dh, dl = _pairs(dyt)
+    xh, xl = _pairs(xt)
+    outs = []
+    for b_ in (emu.gemm_tc, orc.gemm):
+        part = torch.full((G * n_out, k_out), float("nan"))
+        kw = dict(groups=G, a_group=(G, chunk, 1, 0), b_group=(G, chunk, 1, 0), a_rows=n_out, b_rows=k_out, lda=ld, ldb=ld,
+                  precision=prec, out_f32=part, ldo=k_out, group_rows=n_out)
+        if b_ is emu.gemm_tc:
+            kw["variant"] = variant
+        b_(dh, None if prec else dl, xh, None if prec else xl, n_out, k_out, chunk, **kw)
+        outs.append(part.view(G, n_out, k_out).sum(0))
+    _close(outs[0], outs[1], 5e-5)
+    assert (outs[0] - dyt[:, :rows] @ xt[:, :rows].t()).abs().max() < (2e-3 if prec == 0 else 0.2)
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+def test_fused_attention_kernel(be, prec):
+    """14 warps, ten mbarrier families, S and O double-buffered in tensor memory, P as the TS-form A operand, lazy rescale;
+    2 frames = 80 work items on the emulated 6-SM device, i.e. ~13 items per persistent CTA (phase parities wrap)"""
+    emu, orc = be
+    torch.manual_seed(30 + prec)
+    frames = 2
+    qk = torch.randn(frames * 576, 2048) * 1.5
+    qk[:576, :1024] *= 4.0                    # frame 0: large score spread -> exercises the lazy O rescale
+    vt = torch.randn(frames * 8 * 128, 576)
+    qh, ql = _pairs(qk)
+    vh, vl = _pairs(vt)
+    res = []
+    for fn in (emu.attention_tc, orc.attention):
+        ch = torch.full((frames * 576, 1024), float("nan"), dtype=BF16)
+        cl = None if prec else torch.full((frames * 576, 1024), float("nan"), dtype=BF16)
+        fn(qh, None if prec else ql, vh, None if prec else vl, ch, cl, frames, prec)
+        res.append(ch.float() + (0 if prec else cl.float()))
+    assert not torch.isnan(res[0]).any()
+    _close(res[0], res[1], 1.5e-2 if prec else 1e-4)
+
+
+def test_deadlock_detector_and_handoff_selftest():
+    """the emulation's own check: a correct mbarrier hand-off runs to completion, one wait on the wrong phase parity is
+    reported as a deadlock (abort), not a hang and not a pass"""
+    code = (
+        "import ctypes as C, sys; sys.path.insert(0, %r); import build_emu\n"
+        "L = C.CDLL(build_emu.build()); out = C.c_int(0)\n"
+        "L.emu_selftest_handoff(10, -1, C.byref(out)); print('sum', out.value, flush=True)\n"
+        "L.emu_selftest_handoff(10, int(sys.argv[1]), C.byref(out)); print('survived', flush=True)\n"
+        % os.path.join(os.path.dirname(__file__), "cuda_emu"))
+    r = subprocess.run([sys.executable, "-c", code, "4"], capture_output=True, text=True, timeout=120)
+    assert "sum %d" % sum(100 + i for i in range(10)) in r.stdout
+    assert "survived" not in r.stdout and r.returncode != 0 and "DEADLOCK" in r.stderr, (r.stdout, r.stderr[-300:])
+
+
+def test_whole_training_step_on_product_kernel_source():
+    """forward + loss + backward with EVERY launch -- tcgen05 GEMMs (all operand / group / epilogue patterns of the
+    engine), fused attention, and all bandwidth kernels -- executed from the product's own kernel source on the
+    emulation, fp32-parity operand mode, against torch.autograd on the restated forward"""
+    emu, _ = build_emu.make_backend(real_tensor_core=True)
+    preset, batch = "UnrealEgo", 1
+    sd = weights.make_state_dict(preset, seed=5)
+    params = {k: v.clone().contiguous() for k, v in sd.items()}
+    eng = training.TrainEngine(preset, params, precision="bf16x3", backend=emu)
+    eng.use_tape = False
+    x = synthetic_heatmaps(preset, batch, seed=17, kind="gauss")
+    gt = torch.randn(batch, 16, 3, generator=torch.Generator().manual_seed(19)) * 20
+    ref_loss, _, _, ref_grads = tro.train_step(sd, x, gt, preset)
+    eng.forward(x.clone())
+    loss = eng.loss_and_grad(gt.clone())
+    grads = eng.backward()
+    assert abs(float(loss[0]) - float(ref_loss)) < 2e-5 * max(1.0, abs(float(ref_loss)))
+    assert not torch.isnan(eng.flat_grad).any()
+    for k, g_ref in ref_grads.items():
+        if g_ref is None or g_ref.abs().max() < 1e-7:
+            continue
+        a, b = grads[k].flatten().double(), g_ref.flatten().double()
+        assert float((a @ b) / (a.norm() * b.norm())) > 0.9995, k
+        assert abs(float(a.norm() / b.norm()) - 1) < 2e-2, k
