@@ -57,11 +57,16 @@ inline std::atomic<long long>& launch_counter() {
   (eb_emu::launch_ex(dim3(grid), dim3(block), (cluster), (smem), [=]() { kernel(__VA_ARGS__); }), cudaSuccess)
 #define EB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
   eb_emu::launch_ex(dim3(grid), dim3(block), 1, (smem), [=]() { kernel(__VA_ARGS__); })
+#define EB_LAUNCH_GRID_SYNC(kernel, grid, block, smem, stream, ...) \
+  eb_emu::launch_ex(dim3(grid), dim3(block), int(grid), (smem), [=]() { kernel(__VA_ARGS__); })
 #else
 #define EB_SET_MAX_SMEM(kernel, bytes) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
 #define EB_LAUNCH_CLUSTER(kernel, grid, block, smem, cluster, stream, ...) \
   eb::launch_cluster(kernel, grid, block, smem, cluster, stream, __VA_ARGS__)
 #define EB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// kernels whose CTAs synchronise through global memory: every CTA of the grid must be co-resident (the caller sizes the
+// grid accordingly); the emulation runs the whole grid concurrently
+#define EB_LAUNCH_GRID_SYNC(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
 #ifdef EB_HOST_EMU

@@ -129,7 +129,7 @@ int pose_metrics_run(const float* pred, const float* gt, long long frames, int n
   EB_REQUIRE(nj >= 3 && nj <= 32, "pose_metrics: joints must be in [3, 32], got %d", nj);
   if (frames == 0) return 0;
   ProfScope prof("pose_metrics_kernel", stream);
-  pose_metrics_kernel<<<(unsigned)((frames + 7) / 8), 256, 0, stream>>>(pred, gt, frames, nj, unit_scale, mpjpe, pa_mpjpe);
+  EB_LAUNCH_COOP(pose_metrics_kernel, (unsigned)((frames + 7) / 8), 256, stream, pred, gt, frames, nj, unit_scale, mpjpe, pa_mpjpe);
   EB_CHECK_LAUNCH("pose_metrics_kernel");
   return 0;
 }

@@ -52,6 +52,14 @@ template <int N>
 __device__ __forceinline__ void named_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N) : "memory");
 }
+// generic-proxy writes (st.global / st.shared of this thread) -> visible to later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// acquire load at GPU scope (polling a global-memory barrier counter)
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

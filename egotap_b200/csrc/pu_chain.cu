@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(192, 1)
 pu_chain_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                 const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl, const PuParams p) {
   using C = PuCfg<NSPLIT>;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sW = smem;
   uint8_t* sA = smem + C::W_BYTES;
@@ -233,20 +233,20 @@ pu_chain_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant_
     }
     // ---------------------------------------------------------------- group barrier between joints
     if (t + 1 < p.J) {
-      asm volatile("fence.proxy.async;" ::: "memory");   // this thread's st.global -> later TMA (async proxy) reads
+      fence_proxy_async_all();   // this thread's st.global -> later TMA (async proxy) reads
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");
+        fence_proxy_async_all();
         atomicAdd(p.counters + bg, 1u);
         const unsigned int want = PC_SLICES * (t + 1);
         const long long t0 = clock64();
         unsigned int seen;
         do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + bg) : "memory");
+          seen = ld_acquire_gpu_u32(p.counters + bg);
           if (clock64() - t0 > EB_WAIT_TIMEOUT_CYCLES) { printf("egotap_b200: pu_chain group barrier timeout\n"); __trap(); }
         } while (seen < want);
-        asm volatile("fence.proxy.async;" ::: "memory");
+        fence_proxy_async_all();
       }
       __syncthreads();
     }
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(128) pu_permute_split_kernel(const float* __re
 
 int pu_permute_split_run(const float* W, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream) {
   ProfScope prof("pu_permute_split_kernel", stream);
-  pu_permute_split_kernel<<<4 * PC_H, 128, 0, stream>>>(W, hi, lo);
+  EB_LAUNCH(pu_permute_split_kernel, 4 * PC_H, 128, stream, W, hi, lo);
   EB_CHECK_LAUNCH("pu_permute_split_kernel");
   return 0;
 }
@@ -286,11 +286,11 @@ static int launch_pu(const CUtensorMap* tm, const PuParams& p, int groups, cudaS
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
   if (!attr_done[dev_]) {
-    EB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    EB_CUDA(EB_SET_MAX_SMEM(kern, C::SMEM_BYTES));
     attr_done[dev_] = true;
   }
   ProfScope prof("pu_chain_kernel", stream);
-  kern<<<groups * PC_SLICES, 192, C::SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  EB_LAUNCH_GRID_SYNC(kern, groups * PC_SLICES, 192, C::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3], p);
   EB_CHECK_LAUNCH("pu_chain_kernel");
   return 0;
 }

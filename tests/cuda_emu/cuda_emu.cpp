@@ -5,6 +5,7 @@
 #include <ucontext.h>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <vector>
 
 namespace eb_emu {
@@ -12,12 +13,13 @@ namespace eb_emu {
 uint3 g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
 
+extern int g_num_sms;
 namespace {
 constexpr size_t kStack = 512 * 1024;
 constexpr int kMaxWarps = 64, kNamed = 16;
 struct Fiber {
   ucontext_t ctx;
-  std::vector<char> stack;
+  std::unique_ptr<char[]> stack;          // not zero-filled: pages are touched only as far as the fiber really uses them
   bool done = false;
   int cta = 0, warp = 0, lane = 0, tid = 0;
   // what a blocked fiber waits for, so the scheduler does not switch to it in vain: a barrier generation counter that
@@ -37,7 +39,7 @@ struct Cta {
   unsigned block_gen = 0;
   int warp_live[kMaxWarps], warp_waiting[kMaxWarps];
   unsigned warp_gen[kMaxWarps];
-  float warp_buf[kMaxWarps][32];
+  double warp_buf[kMaxWarps][32];
   int named_waiting[kNamed], named_need[kNamed];
   unsigned named_gen[kNamed];
 };
@@ -109,7 +111,8 @@ uint32_t* tmem_of(int r) { return ctas[r].tmem.data(); }
 uint32_t& tmem_next_col() { return C().tmem_next; }
 int cta_rank() { return cur ? cur->cta : 0; }
 int lane() { return cur ? cur->lane : 0; }
-int num_sms() { return 6; }     // a small "device": persistent kernels then loop over several tiles per CTA
+int g_num_sms = 6;                 // a small "device": persistent kernels then loop over several tiles per CTA
+int num_sms() { return g_num_sms; }
 
 void syncthreads() {
   need_coop("__syncthreads()");
@@ -135,12 +138,12 @@ void cluster_sync() {
   wait_gen(&cluster_gen, gen);
 }
 
-float shfl_xor(float v, int lane_mask) {
+double shfl_xor(double v, int lane_mask) {
   need_coop("warp shuffle");
   Cta& c = C();
   c.warp_buf[cur->warp][cur->lane] = v;
   warp_barrier();
-  const float r = c.warp_buf[cur->warp][cur->lane ^ lane_mask];
+  const double r = c.warp_buf[cur->warp][cur->lane ^ lane_mask];
   warp_barrier();
   return r;
 }
@@ -148,10 +151,10 @@ float shfl_xor(float v, int lane_mask) {
 bool any_sync(bool pred) {
   need_coop("warp vote");
   Cta& c = C();
-  c.warp_buf[cur->warp][cur->lane] = pred ? 1.f : 0.f;
+  c.warp_buf[cur->warp][cur->lane] = pred ? 1.0 : 0.0;
   warp_barrier();
   bool r = false;
-  for (int i = 0; i < 32; ++i) r = r || c.warp_buf[cur->warp][i] != 0.f;   // (all kernels here use full warps)
+  for (int i = 0; i < 32; ++i) r = r || c.warp_buf[cur->warp][i] != 0.0;   // (all kernels here use full warps)
   warp_barrier();
   return r;
 }
@@ -206,14 +209,14 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
       for (int i = 0; i < kNamed; ++i) { c.named_waiting[i] = 0; c.named_need[i] = 1 << 30; }
       for (int t = 0; t < nthreads; ++t) {
         Fiber& f = fibers[k * nthreads + t];
-        if (f.stack.empty()) f.stack.resize(kStack);
+        if (!f.stack) f.stack.reset(new char[kStack]);
         f.done = false;
         f.wait_gen = nullptr; f.wait_phase = nullptr;
         f.cta = k; f.tid = t; f.warp = t / 32; f.lane = t % 32;
         ++c.warp_live[f.warp];
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_stack.ss_sp = f.stack.get();
+        f.ctx.uc_stack.ss_size = kStack;
         f.ctx.uc_link = &sched_ctx;
         makecontext(&f.ctx, trampoline, 0);
       }
@@ -267,28 +270,8 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
 namespace eb {
 bool& prof_on() { static bool off = false; return off; }
 void prof_push(const ProfRec&) {}
-// declared locally in plan.cu (which holds the whole-path plan and is not emulated)
-int ingest_run(const float*, int, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
-int layernorm_run(const float*, const float*, const float*, long long, int, int, float, __nv_bfloat16*, __nv_bfloat16*,
-                  float*, cudaStream_t);
-int head_run(const float*, int, const float*, const float*, const float*, const float*, const float*, long long, int, int,
-             int, float*, cudaStream_t);
 }  // namespace eb
+extern "C" void emu_set_num_sms(int n) { eb_emu::g_num_sms = n; }
 extern "C" const char* egotap_b200_last_error(void) { return eb::err_buf(); }
 extern "C" long long egotap_b200_launch_count(void) { return eb::launch_counter().load(); }
 
-// the op-level entries whose extern "C" wrappers live in plan.cu: same one-line forwarding as there
-extern "C" int egotap_b200_ingest(const float* x, int frames, int preset, void* p_hi, void* p_lo, void* l_hi, void* l_lo,
-                                  void* stream) {
-  return eb::ingest_run(x, frames, preset == EGOTAP_PRESET_UNREALEGO ? 15 : 17, (__nv_bfloat16*)p_hi, (__nv_bfloat16*)p_lo,
-                        (__nv_bfloat16*)l_hi, (__nv_bfloat16*)l_lo, (cudaStream_t)stream);
-}
-extern "C" int egotap_b200_layernorm(const float* x, const float* w, const float* b, long long frames, int rows_in,
-                                     int rows_out, float eps, void* hi, void* lo, float* out_f32, void* stream) {
-  return eb::layernorm_run(x, w, b, frames, rows_in, rows_out, eps, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, out_f32,
-                           (cudaStream_t)stream);
-}
-extern "C" int egotap_b200_head(const float* e, int e_ld, const float* skel, const float* Wp, const float* bp,
-                                const float* Wg, const float* bg, long long frames, int J, float* pose, void* stream) {
-  return eb::head_run(e, e_ld, skel, Wp, bp, Wg, bg, frames, J, 256, 512, pose, (cudaStream_t)stream);
-}

@@ -35,7 +35,8 @@ void syncthreads();
 void syncwarp();
 void named_barrier(int id, int nthreads);
 void cluster_sync();
-float shfl_xor(float v, int lane_mask);
+double shfl_xor(double v, int lane_mask);
+inline float shfl_xor(float v, int lane_mask) { return float(shfl_xor(double(v), lane_mask)); }   // exact round trip
 bool any_sync(bool pred);
 void wait_phase(const void* mbar_first_word, unsigned parity);   // block until the mbarrier phase bit != parity
 void yield_wait();              // a spinning wait gives the other fibers a turn (and feeds the deadlock detector)
@@ -67,6 +68,13 @@ int num_sms();
 #define __ldg(p) (*(p))
 #define __expf(x) expf(x)
 inline float atomicAdd(float* p, float v) { const float old = *p; *p = old + v; return old; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; eb_emu::note_progress(); return old; }
+#define __threadfence() ((void)0)
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+#define clock64() (0LL)
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)

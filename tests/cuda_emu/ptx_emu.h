@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#define EB_WAIT_TIMEOUT_CYCLES (1LL << 62)
 #define EB_DYN_SMEM(name) uint8_t* name = eb_emu::dyn_smem()
 #define EB_DYN_SMEM_1K(name) uint8_t* name = eb_emu::dyn_smem()
 
@@ -38,6 +39,8 @@ inline uint32_t cluster_ctarank() { return uint32_t(eb_emu::cta_rank()); }
 inline void cluster_sync_all() { eb_emu::cluster_sync(); }
 inline uint32_t mapa(uint32_t addr, uint32_t cta) { return (addr & 0xFFFFFF) | ((cta + 1) << 24); }
 inline void fence_proxy_async_smem() {}
+inline void fence_proxy_async_all() {}
+inline uint32_t ld_acquire_gpu_u32(const unsigned int* p) { eb_emu::yield_wait(); return *p; }   // every poll yields
 template <int N>
 inline void named_bar_sync(int id) { eb_emu::named_barrier(id, N); }
 

@@ -241,3 +241,117 @@ def test_whole_training_step_on_product_kernel_source():
         a, b = grads[k].flatten().double(), g_ref.flatten().double()
         assert float((a @ b) / (a.norm() * b.norm())) > 0.9995, k
         assert abs(float(a.norm() / b.norm()) - 1) < 2e-2, k
+
+
+def _emu_lib():
+    import ctypes as C
+    lib = C.CDLL(build_emu.build())
+    lib.egotap_b200_last_error.restype = C.c_char_p
+    return lib
+
+
+@pytest.mark.parametrize("frames,J,x3", [(5, 15, True), (40, 17, False)])
+def test_persistent_chain_kernel(frames, J, x3):
+    """pu_chain_kernel: 32 CTAs that keep their W_hh slice resident in shared memory and meet at a global-memory barrier
+    after every joint (the emulation runs the whole grid concurrently) vs the cell recurrence of the reference
+    (custom_cells.py:94-120)"""
+    import ctypes as C
+    lib = _emu_lib()
+    lib.emu_set_num_sms(32)
+    try:
+        torch.manual_seed(1)
+        H = 512
+        W = (torch.randn(4 * H, H) / H ** 0.5).contiguous()
+        G, Fg = torch.randn(frames * J, 4 * H), torch.randn(frames * J, H)
+        wh, wl = torch.empty(4 * H, H, dtype=BF16), torch.empty(4 * H, H, dtype=BF16)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        assert lib.egotap_b200_pu_permute_split(p(W), p(wh), p(wl), None) == 0
+        out = torch.full((frames * J, H), float("nan"))
+        hg_h, hg_l = torch.zeros(2 * frames, H, dtype=BF16), torch.zeros(2 * frames, H, dtype=BF16)
+        cnt = torch.zeros(64, dtype=torch.int32)
+        lib.egotap_b200_pu_chain.argtypes = ([C.c_void_p] * 3 + [C.c_longlong] * 2 + [C.c_void_p] + [C.c_longlong] * 2 +
+                                             [C.c_void_p] * 6 + [C.c_int] * 3 + [C.c_void_p])
+        rc = lib.egotap_b200_pu_chain(p(wh), p(wl) if x3 else None, p(G), J * 4 * H, 4 * H, p(Fg), J * H, H, p(out), None, None,
+                                      p(hg_h), p(hg_l) if x3 else None, p(cnt), frames, J, 0 if x3 else 1, None)
+        assert rc == 0, lib.egotap_b200_last_error()
+    finally:
+        lib.emu_set_num_sms(6)
+    Wd = (W if x3 else W.to(BF16).float()).double()
+    h = torch.zeros(frames, H, dtype=torch.float64)
+    c = torch.zeros_like(h)
+    Gd, Fd = G.double().view(frames, J, -1), Fg.double().view(frames, J, -1)
+    ref = []
+    for t in range(J):
+        hgate = torch.sigmoid(Fd[:, t]) * h
+        if not x3:
+            hgate = hgate.float().to(BF16).double()
+        g = Gd[:, t] + hgate @ Wd.t()
+        fg, ig, cg, og = g.chunk(4, 1)
+        c = c * torch.sigmoid(fg) + torch.sigmoid(ig) * torch.tanh(cg)
+        h = torch.sigmoid(og) * torch.tanh(c)
+        ref.append(h)
+    ref = torch.stack(ref, 1).reshape(frames * J, H)
+    assert not torch.isnan(out).any()
+    assert (out.double() - ref).abs().max().item() < (2e-5 if x3 else 2e-3)
+
+
+@pytest.mark.parametrize("preset,env", [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
+                                        ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"})])
+def test_whole_inference_path_on_product_source(preset, env, state_dicts):
+    """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
+    from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
+    attention, persistent chain, last-layer dummy-row skipping) and the A/B switches.  Runs in a subprocess because the
+    switches are read from the environment once per process."""
+    import json
+    code = r'''
+import ctypes as C, json, os, sys
+sys.path[:0] = %r
+import torch, build_emu, egotap_oracle as orc, weights
+from egotap_b200.synthetic import synthetic_heatmaps
+preset = %r
+lib = C.CDLL(build_emu.build()); lib.egotap_b200_last_error.restype = C.c_char_p; lib.egotap_b200_param_name.restype = C.c_char_p
+lib.emu_set_num_sms(32)
+pid = 0 if preset == "UnrealEgo" else 1
+pb, wb = C.c_size_t(), C.c_size_t()
+lib.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+assert lib.egotap_b200_plan_sizes(pid, 0, 1, C.byref(pb), C.byref(wb)) == 0
+packed = torch.zeros(pb.value + 1024, dtype=torch.uint8); work = torch.full((wb.value // 4 + 256,), float("nan"))
+al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
+plan = C.c_void_p()
+lib.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+assert lib.egotap_b200_plan_create(pid, 0, 1, al(packed), al(work), C.byref(plan)) == 0
+sd = weights.make_state_dict(preset, seed=5)
+names = [lib.egotap_b200_param_name(pid, i).decode() for i in range(lib.egotap_b200_num_params(pid))]
+tens = [sd[n].float().contiguous() for n in names]
+arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+lib.egotap_b200_pack_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+assert lib.egotap_b200_pack_weights(plan, arr, len(tens), None) == 0, lib.egotap_b200_last_error()
+x = synthetic_heatmaps(preset, 1, seed=1234, kind="gauss").contiguous()
+nj = 16 if preset == "UnrealEgo" else 17
+pose = torch.full((1, nj, 3), float("nan"))
+lib.egotap_b200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+assert lib.egotap_b200_forward(plan, x.data_ptr(), 1, pose.data_ptr(), -1, None) == 0, lib.egotap_b200_last_error()
+with torch.no_grad():
+    ref = orc.forward(sd, x, preset)
+print("RESULT " + json.dumps(orc.parity_report(pose, ref)))
+''' % ([os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
+        os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu")], preset)
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=1500)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep       # the GPU parity tests' own bounds
+
+
+def test_pose_metrics_kernel():
+    import ctypes as C
+    import metrics_oracle as mo
+    lib = _emu_lib()
+    torch.manual_seed(5)
+    pred, gt = torch.randn(19, 16, 3) * 20, torch.randn(19, 16, 3) * 20
+    m, pa = torch.full((19,), float("nan")), torch.full((19,), float("nan"))
+    lib.egotap_b200_pose_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.egotap_b200_pose_metrics(pred.data_ptr(), gt.data_ptr(), 19, 16, 10.0, m.data_ptr(), pa.data_ptr(), None) == 0
+    ref_m, ref_pa = mo.pose_metrics(pred, gt)
+    assert (m - ref_m).abs().max() < 1e-3 and (pa - ref_pa).abs().max() < 1e-3
