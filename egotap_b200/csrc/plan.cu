@@ -27,11 +27,17 @@ int head_run(const float*, int, const float*, const float*, const float*, const 
 int bn_fold_run(const float*, const float*, const float*, const float*, const float*, int, float*, float*, cudaStream_t);
 int vec_add3_run(const float*, const float*, const float*, float*, int, cudaStream_t);
 int pos_permute_run(const float*, const float*, int, int, float*, float*, cudaStream_t);
+// train_ops.cu (shared with the training step)
+int reduce_partials_run(const float*, int, long long, float*, cudaStream_t);
+int bn_apply_run(const float*, long long, int, const float*, const float*, __nv_bfloat16*, __nv_bfloat16*, long long, float*,
+                 long long, int, int, cudaStream_t);
 
 constexpr int HID = 1024, HEADS = 8, HDIM = 128, TOK = 576, MLP = 4096, EMB = 128, PUH = 512, PUX = 256;
 constexpr int NLAYERS = 3;
 
 static bool fused_attention();
+static bool small_batch_splitk();
+constexpr int SPLITK_MAX_FRAMES = 32, SPLITK_MAX_G = 8;
 
 struct W2 {  // bf16 hi/lo weight matrix [N][K]
   __nv_bfloat16* hi = nullptr;
@@ -94,7 +100,7 @@ static std::vector<std::string> param_names(int preset) {
 struct Plan {
   int preset, precision, nsplit, max_batch;
   int J, n_hm, grid, live, nj;
-  bool global_head, packed_ok = false, fused_attention_layout = true;
+  bool global_head, packed_ok = false, fused_attention_layout = true, splitk_layout = false;
   std::vector<std::string> names;
   // ---- packed weights
   W2 w_patch;
@@ -115,7 +121,7 @@ struct Plan {
   size_t packed_bytes;
   // ---- workspace
   W2 a_patch, a_limb, ln, qk, vt, P, ctx, mlp, fin, f1, f2, xb, hg, h0b;
-  float *hidden, *S, *E, *F0, *G0, *gates, *cst, *H0, *FG1, *skel;
+  float *hidden, *S, *E, *F0, *G0, *gates, *cst, *H0, *FG1, *skel, *skp = nullptr, *sky = nullptr;
   unsigned int* counters;
   size_t workspace_bytes;
 
@@ -201,6 +207,11 @@ struct Plan {
     h0b = take2(w, B * J * PUH);
     FG1 = w.take<float>(B * J * 5 * PUH);
     skel = w.take<float>(B * J * PUH);
+    if (splitk_layout) {   // split-K partial products / sums of the first FC block at small batches (EGOTAP_SPLITK=1)
+      const size_t Bs = B < size_t(SPLITK_MAX_FRAMES) ? B : size_t(SPLITK_MAX_FRAMES);
+      skp = w.take<float>(Bs * n_hm * 2048 * SPLITK_MAX_G);
+      sky = w.take<float>(Bs * n_hm * 2048);
+    }
     workspace_bytes = w.off + 256;
   }
 };
@@ -221,6 +232,7 @@ static int plan_init(Plan& pl, int preset, int precision, int max_batch) {
   pl.live = pl.n_hm * 16;
   pl.names = param_names(preset);
   pl.fused_attention_layout = fused_attention();
+  pl.splitk_layout = small_batch_splitk();
   return 0;
 }
 
@@ -230,6 +242,18 @@ static bool fused_attention() {
   if (v < 0) {
     const char* e = getenv("EGOTAP_ATTN");
     v = (e && std::string(e) == "unfused") ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// EGOTAP_SPLITK=1 (opt-in, unmeasured): at small batches the first FC block of both encoders (K = 16384 / 8192, only
+// B*2J rows) is a handful of tiles; cut its reduction dimension into G groups so that >= 128 CTAs stream the weight
+// matrix, sum the partial products and apply the folded BatchNorm + LeakyReLU in a separate bandwidth-bound pass
+static bool small_batch_splitk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EGOTAP_SPLITK");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
@@ -441,8 +465,28 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
     const W2& a0 = enc == 0 ? pl.fin : pl.a_limb;
     const int R = B * n_hm;
     EpiParams e = epi0();
-    e.scale = f[0].scale; e.bias = f[0].shift; e.act = ACT_LRELU; e.out_hi = pl.f1.hi; e.out_lo = pl.f1.lo; e.ldo = 2048;
-    RC(linear(pl, a0, f[0].k, R, f[0].k, f[0].w, 2048, e, st));
+    int G = 1;
+    if (pl.splitk_layout && B <= SPLITK_MAX_FRAMES) {
+      const int tiles = ((R + 127) / 128) * (2048 / 128);
+      G = (148 + tiles - 1) / tiles;
+      if (G > SPLITK_MAX_G) G = SPLITK_MAX_G;
+      while (G > 1 && f[0].k % (64 * G) != 0) --G;
+    }
+    if (G > 1) {
+      const int Kc = f[0].k / G;
+      GemmOperand A{a0.hi, a0.lo, f[0].k, R, G, Kc, 1, 0};
+      GemmOperand Wt{f[0].w.hi, f[0].w.lo, f[0].k, 2048, G, Kc, 1, 0};
+      e.out_f32 = pl.skp; e.ldo = 2048; e.group_rows = R;
+      GemmShape s{R, 2048, Kc, G, G, 0};
+      RC(gemm_run(A, Wt, s, e, pl.nsplit, -1, st));
+      RC(reduce_partials_run(pl.skp, G, (long long)R * 2048, pl.sky, st));
+      RC(bn_apply_run(pl.sky, R, 2048, f[0].scale, f[0].shift, pl.f1.hi, pl.f1.lo, 2048, nullptr, 0, 0, 0, st));
+      e = epi0();
+    } else {
+      e.scale = f[0].scale; e.bias = f[0].shift; e.act = ACT_LRELU; e.out_hi = pl.f1.hi; e.out_lo = pl.f1.lo; e.ldo = 2048;
+      RC(linear(pl, a0, f[0].k, R, f[0].k, f[0].w, 2048, e, st));
+    }
+    e.act = ACT_LRELU;
     e.scale = f[1].scale; e.bias = f[1].shift; e.out_hi = pl.f2.hi; e.out_lo = pl.f2.lo; e.ldo = 512;
     RC(linear(pl, pl.f1, 2048, R, 2048, f[1].w, 512, e, st));
     e.scale = f[2].scale; e.bias = f[2].shift;

@@ -296,11 +296,13 @@ def test_persistent_chain_kernel(frames, J, x3):
 
 
 @pytest.mark.parametrize("preset,env", [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
-                                        ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"})])
+                                        ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
+                                        ("EgoCap", {"EGOTAP_SPLITK": "1"})])
 def test_whole_inference_path_on_product_source(preset, env, state_dicts):
     """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
     from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
-    attention, persistent chain, last-layer dummy-row skipping) and the A/B switches.  Runs in a subprocess because the
+    attention, persistent chain, last-layer dummy-row skipping), the A/B switches, and the opt-in small-batch split-K of
+    the first FC block.  Runs in a subprocess because the
     switches are read from the environment once per process."""
     import json
     code = r'''
