@@ -8,9 +8,16 @@ import torch
 class GpuOpAdapter:
     name = "cuda"
 
-    def __init__(self):
-        from egotap_b200 import capi
-        self.be = capi.CudaBackend()
+    def __init__(self, backend=None, to_device=None, synchronize=None):
+        """defaults: the CUDA backend on the current device.  (tests/test_train_kernels.py also runs the adapter itself on
+        the CPU -- emulation backend, `to_device` = clone -- so its mirroring / aliasing / copy-back logic is checked
+        before it is trusted on the GPU box)"""
+        if backend is None:
+            from egotap_b200 import capi
+            backend = capi.CudaBackend()
+        self.be = backend
+        self._to_device = to_device or (lambda t: t.cuda())
+        self._sync = synchronize or torch.cuda.synchronize
 
     def __getattr__(self, op):
         fn = getattr(self.be, op)
@@ -23,7 +30,7 @@ class GpuOpAdapter:
                 key = st.data_ptr()
                 if key not in mirrors:
                     host = torch.empty(0, dtype=torch.uint8).set_(st)
-                    mirrors[key] = (host, host.cuda())
+                    mirrors[key] = (host, self._to_device(host))
                 d8 = mirrors[key][1]
                 typed = d8.view(t.dtype)
                 return torch.as_strided(typed, t.size(), t.stride(), t.storage_offset())
@@ -35,7 +42,7 @@ class GpuOpAdapter:
                     return [dev(x) for x in a]
                 return a
             out = fn(*[conv(a) for a in args])
-            torch.cuda.synchronize()
+            self._sync()
             for host, d8 in mirrors.values():
                 host.copy_(d8.cpu())
             return out

@@ -380,3 +380,33 @@ def test_round1_bandwidth_kernels(backends, preset, J):
     v1, v2, v3 = torch.randn(100), torch.randn(100), torch.randn(100)
     a, b = _both(backends, "add3", lambda: [v1, v2, v3, torch.zeros(100), 100])
     _same(a[3], b[3], 1e-6)
+
+
+def test_gpu_adapter_mirroring_logic_on_cpu():
+    """tests/gpu_adapter.py (the vehicle of every [cuda] op test) exercised without a GPU: emulation backend underneath,
+    "device" = a cloned CPU buffer.  Aliasing views of one storage must stay aliased on the mirror and every storage must
+    be copied back."""
+    from gpu_adapter import GpuOpAdapter
+    emu, orc = build_emu.make_backend()
+    ad = GpuOpAdapter(backend=emu, to_device=lambda t: t.clone(), synchronize=lambda: None)
+    torch.manual_seed(3)
+    J, B, H = 15, 3, 512
+    FG = torch.randn(B * J, 5 * H)
+    dOut = torch.randn(B * J, H)
+    C_, Hh = torch.randn(B * J, H), torch.randn(B * J, H)
+    res = []
+    for be_ in (ad, orc):
+        dFG = torch.full((B * J, 5 * H), float("nan"))
+        dhg, dc = torch.randn(B, H, generator=torch.Generator().manual_seed(1)), torch.randn(B, H, generator=torch.Generator().manual_seed(2))
+        dg = _pair(B, 4 * H)
+        # dG and dF are two views of ONE buffer (the layer-1 layout), as the engine passes them
+        be_.pu_cell_bwd(FG[:, H:], J * 5 * H, 5 * H, FG, J * 5 * H, 5 * H, C_, Hh, dOut, dhg, dc, dFG[:, H:], J * 5 * H, 5 * H, dFG,
+                        J * 5 * H, 5 * H, dg[0], dg[1], J - 2, J, B)
+        res.append((dFG, dc, dg[0].float() + dg[1].float()))
+    for a, b in zip(res[0], res[1]):
+        _same(a, b, 1e-4)
+    ps = [torch.randn(70), torch.randn(1001)[1:]]
+    gs, ms, vs = [torch.randn_like(p) for p in ps], [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    before = [p.clone() for p in ps]
+    ad.adamw(ps, gs, ms, vs, 1, 1e-3, 0.9, 0.999, 1e-4, 0.0)
+    assert all(not torch.equal(p, b) for p, b in zip(ps, before)) and all(float(m.abs().max()) > 0 for m in ms)
