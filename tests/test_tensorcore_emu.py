@@ -357,3 +357,20 @@ def test_pose_metrics_kernel():
     assert lib.egotap_b200_pose_metrics(pred.data_ptr(), gt.data_ptr(), 19, 16, 10.0, m.data_ptr(), pa.data_ptr(), None) == 0
     ref_m, ref_pa = mo.pose_metrics(pred, gt)
     assert (m - ref_m).abs().max() < 1e-3 and (pa - ref_pa).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("sms", [2, 148])
+def test_gemm_is_independent_of_the_sm_count(be, sms):
+    """persistent tile loops: many tiles per CTA (2 'SMs': accumulator / ring phase parities wrap many times) and more CTAs
+    than tiles (148) must give the same result"""
+    lib = _emu_lib()
+    lib.emu_set_num_sms(sms)
+    try:
+        torch.manual_seed(40)
+        M, N, K = 700, 768, 256
+        a, b = torch.randn(M, K), torch.randn(N, K)
+        for variant, prec in ((1, 0), (4, 1)):
+            e1, e2 = _run_both(be, a, b, M, N, K, prec, variant, lambda: dict(out_f32=torch.full((M, N), float("nan"))))
+            _close(e1["out_f32"], e2["out_f32"], 2e-5 if prec == 0 else 1e-6)
+    finally:
+        lib.emu_set_num_sms(6)
