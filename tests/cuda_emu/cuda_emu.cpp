@@ -94,6 +94,14 @@ void warp_barrier() {
 }
 }  // namespace
 
+namespace { std::vector<std::function<void()>> deferred; }
+void defer(std::function<void()> op) { deferred.push_back(std::move(op)); }
+static void run_deferred() {
+  // asynchronous operations (TMA, tcgen05.mma, tcgen05.commit) issued during the previous round complete now, in issue
+  // order: a consumer that did not wait for them has already run on stale / poisoned data
+  for (size_t i = 0; i < deferred.size(); ++i) { deferred[i](); ++progress; }
+  deferred.clear();
+}
 void note_progress() { ++progress; }
 void yield_wait() { need_coop("a spinning wait"); yield(); }
 void wait_phase(const void* mbar_word, unsigned parity) {
@@ -224,6 +232,7 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
     int idle_rounds = 0;
     while (cluster_live > 0) {
       const unsigned long long before = progress;
+      run_deferred();
       for (int i = 0; i < cluster * nthreads; ++i) {
         Fiber& f = fibers[i];
         if (f.done) continue;
@@ -259,6 +268,7 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
       }
     }
   }
+  run_deferred();
   in_coop = false;
   cur = nullptr;
 }

@@ -7,8 +7,10 @@
 //     (arrival counts, transaction bytes, phase parity), TMA tiled loads with the 128-byte swizzle and zero fill,
 //     tensor memory, tcgen05.mma (SS and TS forms, cta_group 1 and 2) decoding the real shared-memory / instruction
 //     descriptors, tcgen05.ld / st, clusters -- see ptx_emu.h.  It checks protocol (no deadlock, every wait satisfied),
-//     addressing and arithmetic of the kernel code; asynchronous operations complete immediately, so it cannot see a
-//     MISSING wait, and it says nothing about speed.  The model was calibrated on kernels verified on the B200.
+//     addressing and arithmetic of the kernel code.  Asynchronous operations (TMA loads, MMAs, commits) complete one
+//     scheduler round after issue and a TMA destination is poisoned in between, so a consumer that does not wait computes
+//     on NaN / stale data; proxy fences and memory-ordering subtleties are NOT modelled, and nothing about speed is.
+//     The model was calibrated on kernels verified on the B200.
 //
 // Execution model: thread-block clusters run one after another; every thread of a cooperative launch is a fiber
 // (ucontext), so __syncthreads(), named barriers, warp shuffles, __syncwarp() and mbarrier waits have their real meaning
@@ -40,6 +42,7 @@ inline float shfl_xor(float v, int lane_mask) { return float(shfl_xor(double(v),
 bool any_sync(bool pred);
 void wait_phase(const void* mbar_first_word, unsigned parity);   // block until the mbarrier phase bit != parity
 void yield_wait();              // a spinning wait gives the other fibers a turn (and feeds the deadlock detector)
+void defer(std::function<void()> op);   // an asynchronous operation: runs at the start of the next scheduler round
 void note_progress();           // any state change another fiber may be waiting for
 uint8_t* dyn_smem();            // dynamic shared memory of the running CTA
 uint8_t* smem_of(int cta_rank); // ... of a CTA of the running cluster

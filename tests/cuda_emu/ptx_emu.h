@@ -10,8 +10,9 @@
 //   tcgen05.mma kind::f16    : D[m][n] (+)= sum_k A[m][k] * B[n][k], K = 16 per instruction, operands located through the
 //                              real matrix descriptor (start address, SBO, 128-byte swizzle on the address bits) or, for
 //                              the TS form, packed bf16 pairs in tensor memory; cta_group::2 spans both CTAs of the pair
-// Asynchronous operations complete at issue: a missing wait is NOT detected; a wait that can never be satisfied is
-// (deadlock detector of the fiber scheduler).
+// Asynchronous operations (TMA, MMA, commit) are queued at issue and complete, in order, one scheduler round later; a
+// TMA destination holds bf16 NaN in between.  A missing wait therefore shows up as NaN / stale results, a wait that can
+// never be satisfied as a deadlock (fiber scheduler).  Proxy fences and finer memory-ordering rules are not modelled.
 #pragma once
 #include "cuda_emu.h"
 
@@ -82,11 +83,7 @@ struct EmuTmap {            // lives in the 128 bytes of a CUtensorMap (filled b
 };
 static_assert(sizeof(EmuTmap) <= sizeof(CUtensorMap), "emulated tensor map must fit the opaque storage");
 inline void tma_prefetch_desc(const CUtensorMap*) {}
-inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0, int c1, int c2, int c3) {
-  const EmuTmap* tm = reinterpret_cast<const EmuTmap*>(tm_);
-  if (tm->magic != 0x7e4a0001u) { fprintf(stderr, "ptx_emu: not an emulated tensor map\n"); abort(); }
-  const uint32_t doff = uint32_t(dst - eb_emu::dyn_smem());
-  if (doff % 1024) { fprintf(stderr, "ptx_emu: TMA destination must be 1024-byte aligned for the 128B swizzle\n"); abort(); }
+inline void tma_load_now(uint8_t* dst, const EmuTmap* tm, void* bar, int c0, int c1, int c2, int c3) {
   for (uint32_t r = 0; r < tm->box_rows; ++r)
     for (uint32_t i = 0; i < 64; ++i) {
       const uint64_t k = uint64_t(c0) + i, row = uint64_t(c1) + r;
@@ -98,6 +95,16 @@ inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0,
       memcpy(dst + off, &v, 2);
     }
   mbar_complete_tx(bar, tm->box_rows * 128);
+}
+// asynchronous: the destination is poisoned (bf16 NaN) at issue and filled, with complete_tx, one scheduler round later --
+// a consumer that does not wait on the barrier computes on NaN
+inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0, int c1, int c2, int c3) {
+  const EmuTmap tm = *reinterpret_cast<const EmuTmap*>(tm_);
+  if (tm.magic != 0x7e4a0001u) { fprintf(stderr, "ptx_emu: not an emulated tensor map\n"); abort(); }
+  const uint32_t doff = uint32_t(dst - eb_emu::dyn_smem());
+  if (doff % 1024) { fprintf(stderr, "ptx_emu: TMA destination must be 1024-byte aligned for the 128B swizzle\n"); abort(); }
+  for (uint32_t i = 0; i < tm.box_rows * 64; ++i) { const uint16_t nan = 0x7fc0; memcpy(dst + i * 2, &nan, 2); }
+  eb_emu::defer([=]() { tma_load_now(dst, &tm, bar, c0, c1, c2, c3); });
 }
 inline void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   tma_load_to(reinterpret_cast<uint8_t*>(dst), tm, bar, c0, c1, c2, c3);
@@ -177,37 +184,43 @@ __attribute__((no_sanitize("alignment"))) inline void emu_mma_accumulate(uint32_
   }
 }
 template <int CG>
-inline void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (eb_emu::lane() != 0) return;                        // elect.sync: one issuing thread
+inline void umma_bf16_now(int rank, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int M = int((idesc >> 24) & 31) << 4, N = int((idesc >> 17) & 63) << 3;
   const uint32_t col = tmem_d & 0xFFFF, lane0 = tmem_d >> 16;
   if (((idesc >> 15) & 3) != 0 || col + N > 512 || lane0 != 0) { fprintf(stderr, "ptx_emu: unsupported MMA (idesc %x tmem %x)\n", idesc, tmem_d); abort(); }
   static float A[256 * 16], B[256 * 16];
   if (CG == 1) {
     if (M != 128) { fprintf(stderr, "ptx_emu: cta_group::1 MMA with M = %d\n", M); abort(); }
-    const uint8_t* smem = eb_emu::smem_of(eb_emu::cta_rank());
+    const uint8_t* smem = eb_emu::smem_of(rank);
     emu_load_smem_operand(smem, adesc, M, A);
     emu_load_smem_operand(smem, bdesc, N, B);
-    emu_mma_accumulate(eb_emu::tmem_of(eb_emu::cta_rank()), 0, col, M, N, A, B, accumulate != 0);
+    emu_mma_accumulate(eb_emu::tmem_of(rank), 0, col, M, N, A, B, accumulate != 0);
   } else {
-    if (M != 256 || eb_emu::cta_rank() != 0) { fprintf(stderr, "ptx_emu: cta_group::2 MMA must be issued by the leader with M = 256\n"); abort(); }
+    if (M != 256 || rank != 0) { fprintf(stderr, "ptx_emu: cta_group::2 MMA must be issued by the leader with M = 256\n"); abort(); }
     for (int r = 0; r < 2; ++r) {       // A rows and B rows are split across the pair, at the same shared-memory offsets
       emu_load_smem_operand(eb_emu::smem_of(r), adesc, 128, A + r * 128 * 16);
       emu_load_smem_operand(eb_emu::smem_of(r), bdesc, N / 2, B + r * (N / 2) * 16);
     }
     for (int r = 0; r < 2; ++r) emu_mma_accumulate(eb_emu::tmem_of(r), 0, col, 128, N, A + r * 128 * 16, B, accumulate != 0);
   }
-  eb_emu::note_progress();
+}
+// asynchronous: queued at issue, executed in issue order one scheduler round later (operands are read THEN, so a ring slot
+// that is recycled before the commit that guards it has arrived feeds the MMA the wrong data)
+template <int CG>
+inline void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (eb_emu::lane() != 0) return;                        // elect.sync: one issuing thread
+  const int rank = eb_emu::cta_rank();
+  eb_emu::defer([=]() { umma_bf16_now<CG>(rank, tmem_d, adesc, bdesc, idesc, accumulate); });
 }
 template <int CG>
-inline void umma_commit(uint64_t* bar) {
+inline void umma_commit(uint64_t* bar) {              // arrives once every previously issued MMA has completed
   if (eb_emu::lane() != 0) return;
   if (CG == 1) {
-    mbar_arrive_at(bar);
+    eb_emu::defer([=]() { mbar_arrive_at(bar); });
   } else {
-    const uint32_t a = smem_u32(bar);
-    mbar_arrive_at(smem_ptr(mapa(a, 0)));
-    mbar_arrive_at(smem_ptr(mapa(a, 1)));
+    void* b0 = smem_ptr(mapa(smem_u32(bar), 0));
+    void* b1 = smem_ptr(mapa(smem_u32(bar), 1));
+    eb_emu::defer([=]() { mbar_arrive_at(b0); mbar_arrive_at(b1); });
   }
 }
 inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -229,22 +242,25 @@ inline void tmem_st16(uint32_t taddr, const uint32_t* r) { tmem_st_n(taddr, r, 1
 inline void tmem_st_wait() {}
 // TS form, cta_group::1: A (128 x 16 bf16) from tensor memory -- lane = row, 8 consecutive 32-bit columns, each holding
 // the K-elements (2c, 2c + 1) as a packed bf16 pair with the even one in the low half; B from shared memory
-inline void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (eb_emu::lane() != 0) return;
+inline void umma_bf16_ts_now(int rank, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int M = int((idesc >> 24) & 31) << 4, N = int((idesc >> 17) & 63) << 3;
   const uint32_t col = tmem_d & 0xFFFF, acol = tmem_a & 0xFFFF;
   if (M != 128 || (tmem_d >> 16) != 0 || (tmem_a >> 16) != 0 || col + N > 512 || acol + 8 > 512) { fprintf(stderr, "ptx_emu: unsupported TS MMA\n"); abort(); }
   static float A[128 * 16], B[256 * 16];
-  uint32_t* t = eb_emu::tmem_of(eb_emu::cta_rank());
+  uint32_t* t = eb_emu::tmem_of(rank);
   for (int m = 0; m < 128; ++m)
     for (int c = 0; c < 8; ++c) {
       const uint32_t w = t[m * 512 + acol + c];
       A[m * 16 + 2 * c] = __uint_as_float(w << 16);
       A[m * 16 + 2 * c + 1] = __uint_as_float(w & 0xffff0000u);
     }
-  emu_load_smem_operand(eb_emu::smem_of(eb_emu::cta_rank()), bdesc, N, B);
+  emu_load_smem_operand(eb_emu::smem_of(rank), bdesc, N, B);
   emu_mma_accumulate(t, 0, col, M, N, A, B, accumulate != 0);
-  eb_emu::note_progress();
+}
+inline void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (eb_emu::lane() != 0) return;
+  const int rank = eb_emu::cta_rank();
+  eb_emu::defer([=]() { umma_bf16_ts_now(rank, tmem_d, tmem_a, bdesc, idesc, accumulate); });
 }
 
 }  // namespace eb

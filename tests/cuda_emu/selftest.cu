@@ -37,3 +37,31 @@ extern "C" int emu_selftest_handoff(int rounds, int break_at, int* out) {
   eb_emu::launch_ex(dim3(1), dim3(64), 1, 1024, [=]() { handoff_kernel(rounds, break_at, out); });
   return 0;
 }
+
+// asynchrony self-test: a TMA load whose consumer does / does not wait on the barrier.  Without the wait the consumer
+// must see the poison the emulation puts into the destination at issue (bf16 NaN), not the data.
+#include "host_util.cuh"
+namespace {
+void tma_kernel(CUtensorMap tm, int wait, float* out) {
+  using namespace eb;
+  EB_DYN_SMEM_1K(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 64 * 128);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, 64 * 128);
+    tma_load_4d(smem, &tm, bar, 0, 0, 0, 0);
+    if (wait) mbar_wait(bar, 0);
+    uint16_t v;
+    memcpy(&v, smem, 2);                       // element (row 0, k 0): chunk 0 of row 0 is not moved by the swizzle
+    *out = __uint_as_float(uint32_t(v) << 16);
+  }
+}
+}  // namespace
+
+extern "C" int emu_selftest_tma(const void* src_bf16_64x64, int wait, float* out) {
+  CUtensorMap tm;
+  if (eb::make_operand_tmap(&tm, src_bf16_64x64, 64, 64, 64, 1, 0, 1, 0, 64)) return -1;
+  eb_emu::launch_ex(dim3(1), dim3(32), 1, 64 * 128 + 64, [=]() { tma_kernel(tm, wait, out); });
+  return 0;
+}

@@ -374,3 +374,14 @@ def test_gemm_is_independent_of_the_sm_count(be, sms):
             _close(e1["out_f32"], e2["out_f32"], 2e-5 if prec == 0 else 1e-6)
     finally:
         lib.emu_set_num_sms(6)
+
+
+def test_emulation_models_asynchrony():
+    """TMA loads and MMAs complete one scheduler round after issue; a TMA destination is poisoned in between.  A consumer
+    that waits on the barrier sees the data, one that does not sees NaN -- so a missing wait in a new kernel shows up"""
+    import ctypes as C
+    lib = _emu_lib()
+    src = (torch.arange(64 * 64, dtype=torch.float32).view(64, 64) + 3).to(BF16).contiguous()
+    out = C.c_float(0)
+    assert lib.emu_selftest_tma(C.c_void_p(src.data_ptr()), 1, C.byref(out)) == 0 and out.value == 3.0
+    assert lib.emu_selftest_tma(C.c_void_p(src.data_ptr()), 0, C.byref(out)) == 0 and out.value != out.value   # NaN
