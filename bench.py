@@ -424,6 +424,7 @@ def run_train(args):
     net = net.to(dev).train()
     eng = net.train_engine()
     eng.use_cuda_graph = bool(args.graph) and world == 1
+    eng.persistent_bptt = bool(args.persistent_bptt)
     red = ddp.StagedGradAllReduce(eng) if world > 1 else None
     nj = net.num_joints
     x_host = egotap_b200.synthetic_heatmaps(args.preset, B, seed=1234 + rank, kind="gauss").pin_memory()
@@ -486,6 +487,7 @@ def run_train(args):
                 data="synthetic",
                 config=dict(workload=TRAIN_WORKLOAD % (args.preset, B), preset=args.preset, batch_per_gpu=B, global_batch=total,
                             precision=args.precision, issue="cuda graph" if eng.use_cuda_graph else "recorded-call replay",
+                            chain_backward="persistent kernel" if eng.persistent_bptt else "per-joint launches",
                             parallelism="dp%d (per-rank micro-batch, staged gradient all-reduce over NCCL)" % world,
                             l2="activations + gradients >> 126 MB L2 per step, no flush needed"),
                 e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=x_host.numel() * 4 + gt_host.numel() * 4,
@@ -523,6 +525,8 @@ def main():
                     help="lifting = BASELINE configs 1-3 (default); lifting_gt = the same with the input heatmaps synthesised on "
                          "the GPU from keypoints each step (--use_gt_heatmap path); e2e_rgb = config 4 (RGB -> heatmap nets -> lifting); "
                          "train = config 5 (optimisation step; reference batch size 32, scripts/train/PoseEstimator/*.sh)")
+    ap.add_argument("--persistent-bptt", dest="persistent_bptt", action="store_true",
+                    help="train workload: BPTT of each propagation layer as one persistent launch instead of per-joint launches")
     ap.add_argument("--graph", action="store_true", help="train workload, 1 GPU: run forward+loss+backward from a CUDA graph")
     ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
     args = ap.parse_args()

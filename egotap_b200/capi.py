@@ -28,7 +28,7 @@ EXPORTS = [
     "egotap_b200_colsum", "egotap_b200_reduce_partials", "egotap_b200_gelu_fwd", "egotap_b200_gelu_bwd",
     "egotap_b200_layernorm_bwd", "egotap_b200_softmax_bwd", "egotap_b200_bn_stats", "egotap_b200_bn_apply",
     "egotap_b200_bn_bwd", "egotap_b200_regroup_gather", "egotap_b200_pu_cell_fwd", "egotap_b200_pu_cell_bwd",
-    "egotap_b200_pu_bridge_gate_bwd", "egotap_b200_head_bwd", "egotap_b200_embed_grads", "egotap_b200_pose_loss",
+    "egotap_b200_pu_bridge_gate_bwd", "egotap_b200_pu_chain_bwd", "egotap_b200_head_bwd", "egotap_b200_embed_grads", "egotap_b200_pose_loss",
     "egotap_b200_adamw", "egotap_b200_gt_heatmaps",
 ]
 
@@ -81,6 +81,7 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_regroup_gather": [P, LL, I, LL, I, I, P, P],
         "egotap_b200_pu_cell_fwd": [P, LL, LL, P, LL, LL, P, P, P, P, P, P, I, I, LL, P],
         "egotap_b200_pu_cell_bwd": [P, LL, LL, P, LL, LL, P, P, P, P, P, P, LL, LL, P, LL, LL, P, P, I, I, LL, P],
+        "egotap_b200_pu_chain_bwd": [P, P, P, LL, LL, P, LL, LL, P, P, P, P, LL, LL, P, LL, LL, P, P, P, I, I, I, P],
         "egotap_b200_pu_bridge_gate_bwd": [P, LL, P, LL, I, P, I, LL, P, LL, P],
         "egotap_b200_head_bwd": [P, P, LL, P, P, P, LL, I, P, LL, P, P, P, P, P, P, LL, P],
         "egotap_b200_embed_grads": [P, I, I, P, P, P],
@@ -456,6 +457,12 @@ class CudaBackend:
         self._c("egotap_b200_pu_cell_bwd", _ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all), _ptr(H), _ptr(dOut),
                                              _ptr(dhg), _ptr(dc), _ptr(dG), dg_rs, dg_ts, _ptr(dF), df_rs, df_ts, _ptr(dgp_hi),
                                              _ptr(dgp_lo), t, J, B, self._st())
+
+    def pu_chain_bwd(self, wT_hi, wT_lo, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, dOut, dG, dg_rs, dg_ts, dF, df_rs, df_ts, x_hi,
+                     x_lo, counters, B, J, precision):
+        self._c("egotap_b200_pu_chain_bwd", _ptr(wT_hi), _ptr(wT_lo), _ptr(G), g_rs, g_ts, _ptr(F_), f_rs, f_ts, _ptr(C_all),
+                _ptr(H), _ptr(dOut), _ptr(dG), dg_rs, dg_ts, _ptr(dF), df_rs, df_ts, _ptr(x_hi), _ptr(x_lo), _ptr(counters), B, J,
+                precision, self._st())
 
     def pu_bridge_gate_bwd(self, dE, e_ld, F0, f_ld, f_col, E, X, rows, dF, df_ld):
         self._c("egotap_b200_pu_bridge_gate_bwd", _ptr(dE), e_ld, _ptr(F0), f_ld, f_col, _ptr(E), X, rows, _ptr(dF), df_ld,

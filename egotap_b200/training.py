@@ -155,6 +155,9 @@ class TrainEngine:
         # Opt-in: the same step captured in a CUDA graph (single-GPU; the staged all-reduce stays on the replay path).
         # Step 1 runs eagerly (allocations, per-device kernel attributes), step 2 is captured, later steps replay.
         self.use_cuda_graph = False
+        # Opt-in: BPTT of each propagation layer as ONE persistent launch (csrc/pu_chain_bwd.cu) instead of J x
+        # (cell-backward kernel + dgates . W_hh GEMM); same arithmetic
+        self.persistent_bptt = False
         self._graph, self._graph_key, self._graph_warm = None, None, None
         self._alloc_weights()
         self.scr = self.be.empty((4 * 1024 * 1024,), torch.float32)     # reduction scratch shared by the small ops
@@ -326,6 +329,8 @@ class TrainEngine:
         S["dE"], S["dSkel"], S["dH0"] = f32(RJ, 2 * PUX), f32(RJ, PUH), f32(RJ, PUH)
         S["dFG1"], S["dG0"], S["dF0"] = f32(RJ, 5 * PUH), f32(RJ, 4 * PUH), f32(RJ, PUH + PUX)
         S["dhg"], S["dc"], S["dgp"] = f32(B, PUH), f32(B, PUH), pair(B, 4 * PUH)
+        S["dgx"] = pair(2 * B, 4 * PUH)                       # exchange buffer of the persistent BPTT kernel
+        S["counters"] = self.be.empty((64,), torch.int32)
         S["dpos"] = f32(TOK, HID)
         S["colpart"] = f32(((M + 63) // 64) * MLPD)           # per-tile column sums of transpose_split (bias gradients)
         S["bias_tmp"] = f32(5 * PUH)
@@ -572,6 +577,14 @@ class TrainEngine:
 
     def _chain_bwd(self, B, G, g_ld, F, f_ld, C, H, dOut, dG, dg_ld, dF, df_ld, WhhT):
         J, be, S = self.J, self.be, self.S
+        if self.persistent_bptt:
+            for b0 in range(0, B, 1024):              # 32 CTAs per 256 frames must be co-resident
+                bc = min(1024, B - b0)
+                be.pu_chain_bwd(WhhT.hi, WhhT.lo, _offset(G, b0 * J * g_ld), J * g_ld, g_ld, _offset(F, b0 * J * f_ld), J * f_ld,
+                                f_ld, C[b0 * J:], H[b0 * J:], dOut[b0 * J:], _offset(dG, b0 * J * dg_ld), J * dg_ld, dg_ld,
+                                _offset(dF, b0 * J * df_ld), J * df_ld, df_ld, S["dgx"].hi, S["dgx"].lo, S["counters"], bc, J,
+                                self.precision)
+            return
         for t in range(J - 1, -1, -1):
             be.pu_cell_bwd(G, J * g_ld, g_ld, F, J * f_ld, f_ld, C, H, dOut, S["dhg"], S["dc"], dG, J * dg_ld, dg_ld,
                            dF, J * df_ld, df_ld, S["dgp"].hi, S["dgp"].lo, t, J, B)

@@ -240,6 +240,13 @@ int egotap_b200_pu_cell_bwd(const float* G, long long g_rs, long long g_ts, cons
                             const float* C, const float* H, const float* dOut, const float* dhg, float* dc, float* dG,
                             long long dg_rs, long long dg_ts, float* dF, long long df_rs, long long df_ts, void* dgp_hi,
                             void* dgp_lo, int t, int J, long long frames, void* stream);
+/* the same BPTT as J x (pu_cell_bwd + dgates . W_hh GEMM) in ONE persistent launch (mirror of egotap_b200_pu_chain):
+ * wT = W_hh^T (512 x 2048) bf16 hi/lo; x = exchange scratch [2][frames][2048] bf16 hi/lo; counters >= ceil(frames/256)
+ * words; frames <= 1024 per call */
+int egotap_b200_pu_chain_bwd(const void* wT_hi, const void* wT_lo, const float* G, long long g_rs, long long g_ts,
+                             const float* F, long long f_rs, long long f_ts, const float* C, const float* H, const float* dOut,
+                             float* dG, long long dg_rs, long long dg_ts, float* dF, long long df_rs, long long df_ts,
+                             void* x_hi, void* x_lo, void* counters, int frames, int J, int precision, void* stream);
 int egotap_b200_pu_bridge_gate_bwd(float* dE, long long e_ld, const float* F0, long long f_ld, int f_col, const float* E, int X,
                                    long long rows, float* dF, long long df_ld, void* stream);
 int egotap_b200_head_bwd(const float* dpose, const float* e, long long e_ld, const float* skel, const float* Wp,

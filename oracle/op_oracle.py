@@ -474,6 +474,19 @@ class OracleBackend:
         flat(dG)[(b * dg_rs + t * dg_ts).view(-1, 1) + torch.arange(4 * Hd).view(1, -1)] = dgates
         store_pair(dgp_hi, dgp_lo, torch.arange(B * 4 * Hd).view(B, 4 * Hd), dgates)
 
+    def pu_chain_bwd(self, wT_hi, wT_lo, G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, dOut, dG, dg_rs, dg_ts, dF, df_rs, df_ts, x_hi,
+                     x_lo, counters, B, J, precision):
+        """BPTT of one layer in one call == for t = J-1 .. 0: pu_cell_bwd, then dhg = dgates . W_hh (wT = W_hh^T pair)"""
+        Hd = 512
+        wt = pair_f32(wT_hi, wT_lo if precision == PREC_BF16X3 else None, (Hd, 4 * Hd), (4 * Hd, 1))
+        dhg, dc = torch.zeros(B, Hd), torch.zeros(B, Hd)
+        for t in range(J - 1, -1, -1):
+            gh = flat(x_hi)[:B * 4 * Hd].view(B, 4 * Hd)
+            gl = None if (x_lo is None or precision != PREC_BF16X3) else flat(x_lo)[:B * 4 * Hd].view(B, 4 * Hd)
+            self.pu_cell_bwd(G, g_rs, g_ts, F_, f_rs, f_ts, C_all, H, dOut, dhg, dc, dG, dg_rs, dg_ts, dF, df_rs, df_ts, gh, gl, t, J, B)
+            if t > 0:
+                dhg = pair_f32(gh, gl, (B, 4 * Hd), (4 * Hd, 1)) @ wt.t()
+
     def pu_bridge_gate_bwd(self, dE, e_ld, F0, f_ld, f_col, E, X, rows, dF, df_ld):
         """backward of pu_bridge_gate: in: dE[r][X + c] = d b' ; out: dE[r][X + c] = d b' * sigmoid(Fb),
         dF[r][f_col + c] = d b' * bridge * sigmoid'(Fb)"""

@@ -385,3 +385,58 @@ def test_emulation_models_asynchrony():
     out = C.c_float(0)
     assert lib.emu_selftest_tma(C.c_void_p(src.data_ptr()), 1, C.byref(out)) == 0 and out.value == 3.0
     assert lib.emu_selftest_tma(C.c_void_p(src.data_ptr()), 0, C.byref(out)) == 0 and out.value != out.value   # NaN
+
+
+@pytest.mark.parametrize("frames,J,x3", [(5, 15, True), (150, 17, False), (260, 15, True)])
+def test_persistent_bptt_kernel(be, frames, J, x3):
+    """pu_chain_bwd_kernel (one launch = BPTT over all joints of a layer, W_hh^T slices resident, one group barrier per
+    joint) vs the per-joint sequence it replaces (pu_cell_bwd + dgates . W_hh), on the layer-1 memory layout ([F | G] rows)"""
+    emu, orc = be
+    lib = _emu_lib()
+    lib.emu_set_num_sms(64)
+    try:
+        torch.manual_seed(50 + frames)
+        H = 512
+        prec = 0 if x3 else 1
+        W = torch.randn(4 * H, H) / H ** 0.5
+        wT_h, wT_l = op_oracle.split(W.t().contiguous())
+        FG = torch.randn(frames * J, 5 * H)
+        Cs, Hs, dOut = torch.randn(frames * J, H), torch.tanh(torch.randn(frames * J, H)), torch.randn(frames * J, H) * 0.1
+        res = []
+        for b_ in (emu, orc):
+            dFG = torch.full((frames * J, 5 * H), float("nan"))
+            xh, xl = torch.zeros(2 * frames, 4 * H, dtype=BF16), torch.zeros(2 * frames, 4 * H, dtype=BF16)
+            cnt = torch.zeros(64, dtype=torch.int32)
+            b_.pu_chain_bwd(wT_h, wT_l if x3 else None, FG[:, H:], J * 5 * H, 5 * H, FG, J * 5 * H, 5 * H, Cs, Hs, dOut, dFG[:, H:],
+                            J * 5 * H, 5 * H, dFG, J * 5 * H, 5 * H, xh, xl if x3 else None, cnt, frames, J, prec)
+            res.append(dFG)
+    finally:
+        lib.emu_set_num_sms(6)
+    assert not torch.isnan(res[0]).any()
+    _close(res[0], res[1], 2e-5 if x3 else 2e-3)
+
+
+def test_engine_with_persistent_bptt_matches_per_joint_path():
+    """the training engine with persistent_bptt: same gradients as with the per-joint backward (everything else equal)"""
+    lib = _emu_lib()
+    lib.emu_set_num_sms(32)
+    try:
+        emu, _ = build_emu.make_backend()
+        preset, batch = "EgoCap", 2
+        sd = weights.make_state_dict(preset, seed=5)
+        x = synthetic_heatmaps(preset, batch, seed=17, kind="gauss")
+        gt = torch.randn(batch, 17, 3, generator=torch.Generator().manual_seed(19)) * 20
+        flats = []
+        for persistent in (False, True):
+            params = {k: v.clone().contiguous() for k, v in sd.items()}
+            eng = training.TrainEngine(preset, params, precision="bf16x3", backend=emu)
+            eng.use_tape = False
+            eng.persistent_bptt = persistent
+            eng.forward(x.clone())
+            eng.loss_and_grad(gt.clone())
+            eng.backward()
+            flats.append(eng.flat_grad.clone())
+    finally:
+        lib.emu_set_num_sms(6)
+    assert not torch.isnan(flats[1]).any()
+    assert (flats[0] - flats[1]).abs().max().item() <= 1e-4 * flats[0].abs().max().item()   # (the kernel drops the lo*lo products)

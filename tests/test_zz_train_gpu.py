@@ -163,6 +163,24 @@ def test_reference_style_loop_on_the_cuda_module():
     assert torch.isfinite(p_eval).all()
 
 
+def test_persistent_bptt_equals_per_joint_backward():
+    """opt-in persistent BPTT kernel (csrc/pu_chain_bwd.cu): same gradients as the per-joint launches it replaces"""
+    preset = "UnrealEgo"
+    flats = []
+    for persistent in (False, True):
+        sd, params, eng = _engine(preset, "bf16x3")
+        eng.persistent_bptt = persistent
+        eng.use_tape = False
+        x, gt = _inputs(preset, 3)
+        eng.forward(x.cuda())
+        eng.loss_and_grad(gt.cuda())
+        eng.backward()
+        torch.cuda.synchronize()
+        flats.append(eng.flat_grad.cpu())
+    assert not torch.isnan(flats[1]).any()
+    assert (flats[0] - flats[1]).abs().max().item() <= 1e-4 * flats[0].abs().max().item()
+
+
 def test_cuda_graph_step_equals_replayed_step():
     """opt-in CUDA-graph issue of forward + loss + backward: step 1 eager, step 2 captured, step 3 replayed"""
     preset = "UnrealEgo"

@@ -16,6 +16,8 @@ for cfg in "bf16 32" "bf16 256" "bf16x3 32"; do
       --dump gpurun_out/r2a_train_$1_b$2.json 2>&1 | tail -1 | cut -c1-1500
 done
 timeout 600 python bench.py --workload train --precision bf16 --batch 32 --steps 10 --warmup 3 --graph 2>&1 | tail -1 | cut -c1-600
+timeout 600 python bench.py --workload train --precision bf16 --batch 32 --steps 10 --warmup 3 --persistent-bptt 2>&1 | tail -1 | cut -c1-600
+timeout 600 python bench.py --workload train --precision bf16 --batch 32 --steps 10 --warmup 3 --persistent-bptt --graph 2>&1 | tail -1 | cut -c1-600
 timeout 600 python bench.py --workload lifting_gt --steps 10 --warmup 3 --dump gpurun_out/r2a_lifting_gt.json 2>&1 | tail -1 | cut -c1-900
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/r2a_launches_train.csv python bench.py --workload train --precision bf16 --batch 32 --steps 1 --warmup 3 \
