@@ -39,7 +39,7 @@ def build(force=False):
     return OUT
 
 
-def make_backend(real_tensor_core=False):
+def make_backend(real_tensor_core=False, all_oracle=False):
     """A backend for training.TrainEngine whose bandwidth-bound ops -- the training kernels and the round-1 kernels of
     csrc/kernels.cu (ingest, LayerNorm, head, packing) -- execute the real kernel source on the CPU emulation; the
     tensor-core kernels (tcgen05 GEMM, fused attention: GPU-verified in round 1, not emulatable) are served by the op
@@ -121,6 +121,15 @@ def make_backend(real_tensor_core=False):
         def gemm_variant_names(self):
             return [lib.egotap_b200_gemm_variant_name(i).decode() for i in range(lib.egotap_b200_gemm_num_variants())]
 
+    if all_oracle:
+        # every op served by the oracle but still recorded call by call: for tests of the engine's record / replay logic
+        # that do not need the (slow) fiber execution of the kernels
+        def served(name):
+            return lambda self, *a, **k: self._py(getattr(orc, name), *a, **k)
+        ops = [n for n in dir(orc) if not n.startswith("_") and callable(getattr(orc, n)) and n not in ("empty", "zero", "copy")]
+        EmuBackend = type("OracleTapeBackend", (EmuBackend,), {n: served(n) for n in ops})
+        EmuBackend.zero = lambda self, t: self._py(orc.zero, t)
+        EmuBackend.copy = lambda self, d, s_: self._py(orc.copy, d, s_)
     return EmuBackend(), orc
 
 

