@@ -5,6 +5,7 @@
 #include <ucontext.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <memory>
 #include <vector>
 
@@ -52,6 +53,23 @@ const std::function<void()>* cur_body = nullptr;
 int cluster_live = 0, cluster_waiting = 0;
 unsigned cluster_gen = 0;
 unsigned long long progress = 0;
+
+// Thread schedule: 0 = ascending thread index (default), 1 = descending, 2 = reshuffled every scheduler round.  CUDA
+// promises no order between threads that are not separated by a barrier, so results must not depend on this; running the
+// same kernel under all three exposes a missing __syncthreads / __syncwarp (or an in-place hazard between the threads of an
+// independent-thread kernel) whichever direction the dependence has.
+int sched_mode = 0;
+uint64_t sched_rng = 0x9E3779B97F4A7C15ull;
+uint32_t rnd() {
+  sched_rng ^= sched_rng << 13; sched_rng ^= sched_rng >> 7; sched_rng ^= sched_rng << 17;
+  return uint32_t(sched_rng >> 32);
+}
+void make_order(std::vector<int>& order, int n) {
+  order.resize(n);
+  for (int i = 0; i < n; ++i) order[i] = sched_mode == 1 ? n - 1 - i : i;
+  if (sched_mode == 2)
+    for (int i = n - 1; i > 0; --i) std::swap(order[i], order[rnd() % unsigned(i + 1)]);
+}
 
 Cta& C() { return ctas[cur->cta]; }
 void yield() { swapcontext(&cur->ctx, &sched_ctx); }
@@ -174,15 +192,25 @@ void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>
   in_coop = false;
   cur = nullptr;
   const int nthreads = int(block.x * block.y * block.z);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        g_blockIdx = make_uint3(bx, by, bz);
-        for (int t = 0; t < nthreads; ++t) {
-          g_threadIdx = make_uint3(unsigned(t), 0, 0);
-          body();
-        }
-      }
+  const long long nblocks = (long long)grid.x * grid.y * grid.z;
+  std::vector<int> torder;
+  make_order(torder, nthreads);
+  for (long long i = 0; i < nblocks; ++i) {
+    // blocks: ascending, descending, or a stride walk coprime with the block count from a random start
+    long long b = sched_mode == 1 ? nblocks - 1 - i : i;
+    if (sched_mode == 2) {
+      static const long long strides[] = {7919, 104729, 1299709};
+      long long st = 1;
+      for (long long c : strides) if (nblocks % c != 0) { st = c; break; }     // prime and not a divisor: coprime
+      b = (i * (st % nblocks) + 17) % nblocks;
+    }
+    g_blockIdx = make_uint3(unsigned(b % grid.x), unsigned((b / grid.x) % grid.y), unsigned(b / ((long long)grid.x * grid.y)));
+    if (sched_mode == 2 && (i & 7) == 0) make_order(torder, nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+      g_threadIdx = make_uint3(unsigned(torder[t]), 0, 0);
+      body();
+    }
+  }
 }
 
 void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const std::function<void()>& body) {
@@ -230,11 +258,14 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
       }
     }
     int idle_rounds = 0;
+    std::vector<int> order;
+    make_order(order, cluster * nthreads);
     while (cluster_live > 0) {
       const unsigned long long before = progress;
       run_deferred();
-      for (int i = 0; i < cluster * nthreads; ++i) {
-        Fiber& f = fibers[i];
+      if (sched_mode == 2) make_order(order, cluster * nthreads);
+      for (int oi = 0; oi < cluster * nthreads; ++oi) {
+        Fiber& f = fibers[order[oi]];
         if (f.done) continue;
         if (f.wait_gen) {
           if (*f.wait_gen == f.wait_val) continue;
@@ -282,6 +313,10 @@ bool& prof_on() { static bool off = false; return off; }
 void prof_push(const ProfRec&) {}
 }  // namespace eb
 extern "C" void emu_set_num_sms(int n) { eb_emu::g_num_sms = n; }
+extern "C" void emu_set_schedule(int mode, unsigned long long seed) {
+  eb_emu::sched_mode = mode;
+  eb_emu::sched_rng = seed ? seed : 0x9E3779B97F4A7C15ull;
+}
 extern "C" const char* egotap_b200_last_error(void) { return eb::err_buf(); }
 extern "C" long long egotap_b200_launch_count(void) { return eb::launch_counter().load(); }
 

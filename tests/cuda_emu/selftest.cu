@@ -65,3 +65,24 @@ extern "C" int emu_selftest_tma(const void* src_bf16_64x64, int wait, float* out
   eb_emu::launch_ex(dim3(1), dim3(32), 1, 64 * 128 + 64, [=]() { tma_kernel(tm, wait, out); });
   return 0;
 }
+
+// schedule self-test: a neighbour exchange through shared memory WITHOUT the barrier between write and read (sync = 0).
+// Which neighbour's value a thread sees then depends on the order the threads run in: the ascending schedule hides the
+// dependence on lower-numbered threads, the descending one the dependence on higher-numbered threads, so the three
+// schedules of the emulation give different answers for the racy kernel and the same answer for the correct one.
+namespace {
+void neighbour_kernel(int sync, int* out) {
+  __shared__ int buf[64];
+  const int t = threadIdx.x;
+  buf[t] = -1;
+  __syncthreads();
+  buf[t] = t;
+  if (sync) __syncthreads();
+  out[t] = buf[(t + 1) & 63] + 1000 * buf[(t + 63) & 63];
+}
+}  // namespace
+
+extern "C" int emu_selftest_neighbours(int sync, int* out64) {
+  eb_emu::launch(dim3(1), dim3(64), true, [=]() { neighbour_kernel(sync, out64); });
+  return 0;
+}

@@ -387,6 +387,54 @@ def test_emulation_models_asynchrony():
     assert lib.emu_selftest_tma(C.c_void_p(src.data_ptr()), 0, C.byref(out)) == 0 and out.value != out.value   # NaN
 
 
+def _set_schedule(mode):
+    import ctypes as C
+    lib = _emu_lib()
+    lib.emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
+    lib.emu_set_schedule(mode, 2024)
+    return lib
+
+
+def test_thread_schedule_selftest():
+    """the emulation can run the threads of a launch in ascending, descending or per-round reshuffled order: a correct
+    kernel gives the same answer under all three, a kernel with a missing __syncthreads does not"""
+    import ctypes as C
+    outs = {}
+    try:
+        for sync in (1, 0):
+            for mode in (0, 1, 2):
+                lib = _set_schedule(mode)
+                out = (C.c_int * 64)()
+                assert lib.emu_selftest_neighbours(sync, out) == 0
+                outs[sync, mode] = list(out)
+    finally:
+        _set_schedule(0)
+    want = [((t + 1) & 63) + 1000 * ((t + 63) & 63) for t in range(64)]
+    assert outs[1, 0] == outs[1, 1] == outs[1, 2] == want
+    assert outs[0, 0] != want and outs[0, 1] != want and outs[0, 0] != outs[0, 1]      # each order hides one direction only
+    assert outs[0, 2] != want
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["reversed", "shuffled"])
+def test_tensor_core_kernels_do_not_depend_on_the_thread_schedule(be, mode):
+    """the warp-specialised kernels (GEMM incl. a paired-SM configuration, fused attention, both persistent chain kernels)
+    with their threads scheduled in descending / reshuffled order: every hand-off between the TMA, MMA, softmax and
+    epilogue warps must be carried by an mbarrier / named barrier, never by the order the warps happen to run in"""
+    try:
+        _set_schedule(mode)
+        test_gemm_tile_configurations(be, 0, 1)
+        test_gemm_tile_configurations(be, 3, 0)
+        test_gemm_epilogue_modes(be, 4, 1)
+        test_fused_attention_kernel(be, 0)
+        test_fused_attention_kernel(be, 1)
+        test_persistent_chain_kernel(5, 15, True)
+        test_persistent_bptt_kernel(be, 5, 15, True)
+        test_persistent_bptt_kernel(be, 150, 17, False)
+        test_pose_metrics_kernel()
+    finally:
+        _set_schedule(0)
+
+
 @pytest.mark.parametrize("frames,J,x3", [(5, 15, True), (150, 17, False), (260, 15, True)])
 def test_persistent_bptt_kernel(be, frames, J, x3):
     """pu_chain_bwd_kernel (one launch = BPTT over all joints of a layer, W_hh^T slices resident, one group barrier per

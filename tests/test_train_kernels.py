@@ -26,12 +26,32 @@ import build_emu  # noqa: E402
 BF16 = torch.bfloat16
 
 
-@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.timeout(600, method="thread")])])
+# "emu-reversed" / "emu-shuffled": the same kernel source with the threads (and blocks) of every launch scheduled in
+# descending / per-round reshuffled order.  CUDA promises no order between threads that no barrier separates, so the results
+# must not change: a missing __syncthreads / __syncwarp or an in-place hazard between threads shows up in one of the orders.
+SCHEDULES = {"emu": 0, "emu-reversed": 1, "emu-shuffled": 2}
+
+
+@pytest.fixture(scope="module", params=list(SCHEDULES) + [pytest.param("cuda", marks=[pytest.mark.gpu, pytest.mark.timeout(600, method="thread")])])
 def backends(request):
-    if request.param == "emu":
-        return build_emu.make_backend()
+    if request.param in SCHEDULES:
+        import ctypes
+        pair = build_emu.make_backend()
+        pair[0].name = "emu"
+        pair[0].schedule = request.param
+        lib = ctypes.CDLL(build_emu.build())
+        lib.emu_set_schedule.argtypes = [ctypes.c_int, ctypes.c_ulonglong]
+        lib.emu_set_schedule(SCHEDULES[request.param], 12345)
+        yield pair
+        lib.emu_set_schedule(0, 0)
+        return
     from gpu_adapter import GpuOpAdapter
-    return GpuOpAdapter(), op_oracle.OracleBackend()
+    yield GpuOpAdapter(), op_oracle.OracleBackend()
+
+
+def _default_schedule_only(backends):
+    if getattr(backends[0], "schedule", "emu") != "emu":
+        pytest.skip("engine-level / host-logic test: run once, on the default thread schedule")
 
 
 def _pair(rows, cols, poison=True):
@@ -267,6 +287,7 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
     emu, _ = backends
     if emu.name != "emu":
         pytest.skip("engine-level GPU parity lives in tests/test_zz_train_gpu.py")
+    _default_schedule_only(backends)
     preset, batch = "UnrealEgo", 1
     sd = weights.make_state_dict(preset, seed=5)
     params = {k: v.clone().contiguous() for k, v in sd.items()}
@@ -299,6 +320,7 @@ def test_recorded_step_replays_identically(backends):
     hot path): two steps (record, replay) must leave exactly the same weights as two steps without"""
     if backends[0].name != "emu":
         pytest.skip("host-side logic; the CUDA engine uses the same code path in tests/test_zz_train_gpu.py")
+    _default_schedule_only(backends)
     emu, _ = build_emu.make_backend(all_oracle=True)      # record / replay is host logic: ops served by the oracle
     preset, batch = "EgoCap", 1
     sd = weights.make_state_dict(preset, seed=5)
