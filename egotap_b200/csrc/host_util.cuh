@@ -221,7 +221,10 @@ inline int make_operand_tmap(CUtensorMap* tm, const void* base, long long K, lon
   if (g1_stride <= 0) g1_stride = g0_stride * g0_count;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15) || ((g0_stride * 2) & 15) || ((g1_stride * 2) & 15))
     return fail(EGOTAP_E_ARG, "TMA operand must be 16-byte aligned (base %p ld %lld)", base, ld);
-  if (K < 1 || rows < 1 || box_rows < 1 || box_rows > 256)
+  // the driver's limits: box <= 256 per dimension, every global dimension <= 2^32, every stride < 2^40 bytes
+  const long long dmax = 1ll << 32, smax = 1ll << 40;
+  if (K < 1 || rows < 1 || box_rows < 1 || box_rows > 256 || K > dmax || rows > dmax || g0_count > dmax || g1_count > dmax ||
+      ld * 2 >= smax || g0_stride * 2 >= smax || g1_stride * 2 >= smax)
     return fail(EGOTAP_E_DRIVER, "cuTensorMapEncodeTiled (emulated) failed: K %lld rows %lld ld %lld box %d", K, rows, ld, box_rows);
   memset(tm, 0, sizeof(*tm));
   EmuTmap* e = reinterpret_cast<EmuTmap*>(tm);

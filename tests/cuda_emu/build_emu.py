@@ -39,7 +39,7 @@ def build(force=False):
     return OUT
 
 
-def make_backend(real_tensor_core=False, all_oracle=False):
+def make_backend(real_tensor_core=False, all_oracle=False, dry=False):
     """A backend for training.TrainEngine whose bandwidth-bound ops -- the training kernels and the round-1 kernels of
     csrc/kernels.cu (ingest, LayerNorm, head, packing) -- execute the real kernel source on the CPU emulation; the
     tensor-core kernels (tcgen05 GEMM, fused attention: GPU-verified in round 1, not emulatable) are served by the op
@@ -130,6 +130,13 @@ def make_backend(real_tensor_core=False, all_oracle=False):
         EmuBackend = type("OracleTapeBackend", (EmuBackend,), {n: served(n) for n in ops})
         EmuBackend.zero = lambda self, t: self._py(orc.zero, t)
         EmuBackend.copy = lambda self, d, s_: self._py(orc.copy, d, s_)
+    if dry:
+        # for emu_set_dry_run(1): every op goes to the library (host-side checks, tensor maps, launch geometry), nothing executes;
+        # buffers are untouched virtual memory, so the engine can be driven at BASELINE.json's full batch sizes
+        EmuBackend = type("DryBackend", (EmuBackend,), dict(
+            empty=lambda self, shape, dtype=None: torch.empty(shape, dtype=dtype or torch.float32),
+            zero=lambda self, t: None, copy=lambda self, d, s_: None,
+            gemm=lambda self, *a, **k: self.gemm_tc(*a, **k), attention=lambda self, *a: self.attention_tc(*a)))
     return EmuBackend(), orc
 
 

@@ -71,6 +71,22 @@ void make_order(std::vector<int>& order, int n) {
     for (int i = n - 1; i > 0; --i) std::swap(order[i], order[rnd() % unsigned(i + 1)]);
 }
 
+// Launch limits of the real device (sm_100a), checked on every launch; with dry_run set the launch ends here, so the host
+// side of a whole step (argument checks, scratch sizing, tensor maps, grid shapes) can be exercised at the full batch sizes
+// of BASELINE.json without executing -- or even touching the memory of -- the kernels.
+int dry_run = 0;
+long long dry_launches = 0;
+void check_launch_limits(dim3 grid, dim3 block, size_t dyn_smem_bytes) {
+  const unsigned long long threads = 1ull * block.x * block.y * block.z;
+  const bool ok = grid.x >= 1 && grid.y >= 1 && grid.z >= 1 && grid.x <= 2147483647u && grid.y <= 65535u && grid.z <= 65535u &&
+                  threads >= 1 && threads <= 1024 && block.z <= 64 && dyn_smem_bytes <= 227u * 1024u;
+  if (!ok) {
+    fprintf(stderr, "cuda_emu: launch outside the device limits: grid (%u, %u, %u) block (%u, %u, %u) dynamic smem %zu\n", grid.x,
+            grid.y, grid.z, block.x, block.y, block.z, dyn_smem_bytes);
+    abort();
+  }
+}
+
 Cta& C() { return ctas[cur->cta]; }
 void yield() { swapcontext(&cur->ctx, &sched_ctx); }
 
@@ -187,6 +203,8 @@ bool any_sync(bool pred) {
 
 void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>& body) {
   if (cooperative) { launch_ex(grid, block, 1, 0, body); return; }
+  check_launch_limits(grid, block, 0);
+  if (dry_run) { ++dry_launches; return; }
   g_blockDim = block;
   g_gridDim = grid;
   in_coop = false;
@@ -214,6 +232,8 @@ void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>
 }
 
 void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const std::function<void()>& body) {
+  check_launch_limits(grid, block, dyn_smem_bytes);
+  if (dry_run) { ++dry_launches; return; }
   g_blockDim = block;
   g_gridDim = grid;
   const int nthreads = int(block.x * block.y * block.z);
@@ -313,6 +333,12 @@ bool& prof_on() { static bool off = false; return off; }
 void prof_push(const ProfRec&) {}
 }  // namespace eb
 extern "C" void emu_set_num_sms(int n) { eb_emu::g_num_sms = n; }
+extern "C" long long emu_set_dry_run(int on) {
+  const long long n = eb_emu::dry_launches;
+  eb_emu::dry_run = on;
+  eb_emu::dry_launches = 0;
+  return n;          // launches that were checked (not executed) since the last call
+}
 extern "C" void emu_set_schedule(int mode, unsigned long long seed) {
   eb_emu::sched_mode = mode;
   eb_emu::sched_rng = seed ? seed : 0x9E3779B97F4A7C15ull;

@@ -346,6 +346,78 @@ print("RESULT " + json.dumps(orc.parity_report(pose, ref)))
     assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep       # the GPU parity tests' own bounds
 
 
+_DRY_CODE = r'''
+import ctypes as C, json, os, sys
+sys.path[:0] = %r
+import torch, build_emu, weights
+from egotap_b200 import training
+kind, preset, B, prec, extra = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5]
+lib = C.CDLL(build_emu.build()); lib.egotap_b200_last_error.restype = C.c_char_p; lib.egotap_b200_param_name.restype = C.c_char_p
+lib.emu_set_dry_run.restype = C.c_longlong
+lib.emu_set_num_sms(148)
+lib.emu_set_dry_run(1)
+J = 15 if preset == "UnrealEgo" else 17
+nj = 16 if preset == "UnrealEgo" else 17
+x = torch.empty(B, 6 * J, 64, 64)
+if kind == "train":
+    be, _ = build_emu.make_backend(dry=True)
+    sd = weights.make_state_dict(preset, seed=5)
+    eng = training.TrainEngine(preset, {k: v.clone().contiguous() for k, v in sd.items()}, precision=prec, backend=be)
+    eng.use_tape = False
+    eng.persistent_bptt = extra == "persistent"
+    eng.forward(x); eng.loss_and_grad(torch.empty(B, nj, 3)); eng.backward(); eng.adamw_step()
+else:
+    pid, pr = (0 if preset == "UnrealEgo" else 1), (0 if prec == "bf16x3" else 1)
+    pb, wb = C.c_size_t(), C.c_size_t()
+    lib.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    assert lib.egotap_b200_plan_sizes(pid, pr, B, C.byref(pb), C.byref(wb)) == 0
+    packed = torch.empty(pb.value + 1024, dtype=torch.uint8); work = torch.empty(wb.value + 1024, dtype=torch.uint8)
+    al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
+    plan = C.c_void_p()
+    lib.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    assert lib.egotap_b200_plan_create(pid, pr, B, al(packed), al(work), C.byref(plan)) == 0
+    sd = weights.make_state_dict(preset, seed=5)
+    names = [lib.egotap_b200_param_name(pid, i).decode() for i in range(lib.egotap_b200_num_params(pid))]
+    tens = [sd[n].float().contiguous() for n in names]
+    arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
+    lib.egotap_b200_pack_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    assert lib.egotap_b200_pack_weights(plan, arr, len(tens), None) == 0, lib.egotap_b200_last_error()
+    pose = torch.empty(B, nj, 3)
+    lib.egotap_b200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    assert lib.egotap_b200_forward(plan, x.data_ptr(), B, pose.data_ptr(), -1, None) == 0, lib.egotap_b200_last_error()
+print("RESULT " + json.dumps(dict(launches=lib.emu_set_dry_run(0), workspace_gb=(wb.value / 1e9 if kind != "train" else None))))
+'''
+
+
+@pytest.mark.parametrize("kind,preset,batch,prec,extra", [
+    ("train", "UnrealEgo", 32, "bf16", "per-joint"),          # BASELINE config 5 at the reference's batch size
+    ("train", "UnrealEgo", 256, "bf16", "persistent"),
+    ("train", "EgoCap", 256, "bf16x3", "per-joint"),
+    ("train", "UnrealEgo", 1024, "bf16", "persistent"),       # 4 batch groups x 32 co-resident CTAs
+    ("infer", "UnrealEgo", 256, "bf16x3", ""),                # BASELINE config 2 (the bench default)
+    ("infer", "EgoCap", 1024, "bf16", ""),                    # config 3 on one GPU
+    ("infer", "UnrealEgo", 32, "bf16x3", "EGOTAP_SPLITK=1"),
+])
+def test_full_size_steps_pass_the_host_checks_and_launch_limits(kind, preset, batch, prec, extra):
+    """Dry run at BASELINE.json's real batch sizes: the whole training step / inference forward is driven through the library
+    with the emulation in dry-run mode -- every host-side argument check (scratch sizing, strides, paddings, co-residency of
+    the persistent kernels), every tensor-map encode (against the driver's dimension / stride limits) and every launch shape
+    (grid.y / z <= 65535, threads <= 1024, dynamic shared memory <= 227 KB) is exercised, the kernels are not executed and
+    their buffers stay untouched virtual memory.  The executing tests cover the arithmetic at small sizes; this covers what
+    only changes with size."""
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = _DRY_CODE % ([os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), os.path.join(here, "cuda_emu")],)
+    e = dict(os.environ)
+    if "=" in extra:
+        e[extra.split("=")[0]] = extra.split("=")[1]
+    r = subprocess.run([sys.executable, "-c", code, kind, preset, str(batch), prec, extra or "-"], capture_output=True, text=True,
+                       env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert rep["launches"] >= (300 if kind == "train" else 38), rep
+
+
 def test_pose_metrics_kernel():
     import ctypes as C
     import metrics_oracle as mo
