@@ -291,8 +291,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(dist, world)
         return
     e2e_ok = bool(torch.isfinite(host_out[-1]).all()) and (host_out[-1][:2].to(dev) - pose[:2]).abs().max().item() < 1e-5
     # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), per-launch CUDA events, one extra step
@@ -359,7 +358,15 @@ def run_ours(args):
         os.makedirs(os.path.dirname(os.path.abspath(args.dump)), exist_ok=True)
         with open(args.dump, "w") as f:
             json.dump(dict(line=line, kernel_launches=all_recs), f, indent=1)
+    _leave(dist, world)
+
+
+def _leave(dist, world):
+    """symmetric teardown: rank 0 still has collective-free work to do (per-kernel profile, JSON line) after the other ranks
+    are finished; everybody meets once more before the process group is destroyed, so that no rank tears its communicator
+    down while a peer is still alive in it"""
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -466,8 +473,7 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(dist, world)
         return
     pk = peaks()
     all_recs = capi.profile_kernels(lambda: (eng.forward(x), eng.loss_and_grad(gt), eng.backward(), eng.adamw_step(lr=0.0)))
@@ -507,8 +513,7 @@ def run_train(args):
         os.makedirs(os.path.dirname(os.path.abspath(args.dump)), exist_ok=True)
         with open(args.dump, "w") as f:
             json.dump(dict(line=line, kernel_launches=all_recs), f, indent=1)
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(dist, world)
 
 
 def main():
