@@ -192,7 +192,10 @@ def test_batchnorm_train(backends, rows, cols, J):
         return [y, rows, cols, scale, shift, *_pair(out_rows, out_cols), out_cols, torch.full((out_rows, out_cols), float("nan")),
                 out_cols, J, 32 if not J else 256]
     a, b = _both(backends, "bn_apply", apply_args)
-    _same(a[5], b[5]); _same(a[6], b[6]); _same(a[8], b[8], 1e-6)
+    # y*scale + shift contracts to one FMA on the device and is two roundings in the oracle: the fp32 value may differ by an ulp,
+    # which can flip the bf16 rounding of `hi` alone -- the pair is compared as hi + lo (~16 mantissa bits), like every other
+    # pair that is the result of arithmetic
+    _same(a[5].float() + a[6].float(), b[5].float() + b[6].float(), 2e-5); _same(a[8], b[8], 1e-6)
     da = torch.randn(rows, cols)
     a, b = _both(backends, "bn_bwd", lambda: [da.clone(), y, rows, cols, scale, shift, mean, rstd, torch.zeros(cols),
                                                torch.zeros(cols), scr])
@@ -246,7 +249,7 @@ def test_bridge_gate_bwd(backends):
     rows = 45
     F0, E, dE, = torch.randn(rows, 768), torch.randn(rows, 512), torch.randn(rows, 512)
     a, b = _both(backends, "pu_bridge_gate_bwd", lambda: [dE.clone(), 512, F0, 768, 512, E, 256, rows, torch.full((rows, 768), float("nan")), 768])
-    _same(a[0], b[0], 1e-6); _same(a[8], b[8], 1e-6)
+    _same(a[0], b[0], 5e-6); _same(a[8], b[8], 5e-6)     # a few ulp: expf / division / FMA contraction differ between libm and the device
 
 
 @pytest.mark.parametrize("preset,J,B", [("UnrealEgo", 15, 7), ("EgoCap", 17, 4)])
