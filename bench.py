@@ -229,6 +229,8 @@ def run_ours(args):
     # ---------------- parity of what is being timed (small sample through the oracle, rank 0)
     parity = None
     if rank == 0:
+        # torchrun exports OMP_NUM_THREADS=1; the other ranks wait at the barrier below while this check runs
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // world))
         with torch.no_grad():
             ref_in = est.pred_heatmap_cat[:2].cpu() if est is not None else x_host[:2]
             ref = orc.forward(sd, ref_in, args.preset)
