@@ -16,41 +16,12 @@
 #include "host_util.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace eb {
 
-#ifndef EB_HOST_EMU      // (the CUDA-on-CPU emulation of the tests provides functional models of these four)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]: the A operand (128 rows x 16 bf16 per MMA = 8 packed 32-bit columns) is read from
-// tensor memory, so it costs no shared-memory bandwidth.  Same calling convention as umma_bf16 (all lanes call).
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-#endif
+// tmem_st32 / tmem_st16 / umma_bf16_ts / tmem_st_wait: ptx.cuh
 
 // Debug-only wait-cycle accounting (tools/attn_trace.sh builds a separate library with -DEB_ATTN_TRACE).
 #ifdef EB_ATTN_TRACE
@@ -424,6 +395,11 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
                   int query_rows, cudaStream_t stream) {
+  // EGOTAP_ATTN=wide (opt-in, A/B): the 128-key-tile structure of attention_wide.cu; read per call so that one process
+  // can compare the two
+  if (const char* e = getenv("EGOTAP_ATTN"))
+    if (strcmp(e, "wide") == 0)
+      return attention_wide_run(qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, B, nsplit, query_rows, stream);
   EB_REQUIRE(query_rows > 0 && query_rows <= AT_TOK, "attention: query_rows must be in (0, 576]");
   const int qtiles = (query_rows + AT_QT - 1) / AT_QT;
   EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");

@@ -1,0 +1,412 @@
+// Fused multi-head self-attention, second structure ("wide" key tiles), sm_100a.  Opt-in: EGOTAP_ATTN=wide.
+//   ctx[b, q, h*128 + :] = softmax(Q K^T / sqrt(128)) V        reference model/modeling_vit.py:233-252
+//
+// Why: in attention.cu every score MMA is 128 x 64 x 16 = 32 tensor-pipe cycles, below the ~55 cycles the issuing warp
+// needs per tcgen05.mma (measured), and the issuing warp makes ~40 mbarrier round trips per work
+// item.  Here every MMA is 128 x 128 x 16 (64 cycles of math) and the hand-offs are cut to ~26 per item:
+//   * 128-key score tiles (576 keys = 4 full tiles + one 64-key tile, issued with N = 64);
+//   * P_g is written over the columns of S_g (same tensor-memory buffer: S 128 fp32 columns -> P 64 hi + 64 lo packed
+//     bf16x2 columns), so TMEM holds S/P 2 x 128 + O 2 x 128 = 512 columns;
+//   * no "S buffer free" / "P buffer free" barriers: S_{g+2} is issued after PV_g in program order and tcgen05.mma
+//     instructions of one CTA execute in issue order, so S_{g+2} cannot overwrite P_g before PV_g has read it
+//     (the one hardware assumption this kernel adds to those of attention.cu; the softmax warps never touch buffer
+//     g & 1 between their p_full arrive for tile g and the s_full of tile g + 2);
+//   * one software pipeline over the GLOBAL tile sequence of a persistent CTA (5 tiles per work item, buffers alternate
+//     across item boundaries):  S_0; for g: { S_{g+1}; PV_g }  -- the score MMAs of the next item's first tile run
+//     while the softmax warps finish the current item.
+// Shared memory: Q tile (hi/lo) + a ring of 32 KB granules (one 64-wide d block of a 128-key K tile, or one 64-key
+// block of a V^T tile), consumed in MMA order.
+//   warp 0   TMA producer      warp 1   MMA issuer      warps 2-9  softmax (pairs split the keys of a tile)
+//   warps 10-13  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
+#include "gemm.cuh"
+#include "host_util.cuh"
+#include "internal.h"
+
+namespace eb {
+
+constexpr int AW_TOK = 576, AW_HEADS = 8, AW_D = 128, AW_QT = 128, AW_KT = 128;
+constexpr int AW_NT = (AW_TOK + AW_KT - 1) / AW_KT;          // 5 key tiles, the last one has 64 keys
+constexpr int AW_LAST_KEYS = AW_TOK - (AW_NT - 1) * AW_KT;   // 64
+constexpr int AW_THREADS = 64 + 256 + 128;                   // TMA + MMA warps, 8 softmax warps, 4 epilogue warps
+static_assert(AW_LAST_KEYS == 64, "the last key tile is issued with N = 64");
+
+template <int NSPLIT>
+struct AttnWideCfg {
+  static constexpr int NOPS = NSPLIT == 1 ? 1 : 2;
+  static constexpr int BLK = 128 * 64 * 2;                   // 128 rows x 64 bf16 (128-byte rows): 16 KB
+  static constexpr int Q_BYTES = NOPS * 2 * BLK;             // [hi d0-63][hi d64-127][lo d0-63][lo d64-127]
+  static constexpr int GRAN_BYTES = NOPS * BLK;              // K granule: [hi][lo] of one d block; V^T granule: [hi][lo] of one key block
+  static constexpr int NSLOTS = NSPLIT == 1 ? 8 : 4;
+  static constexpr int BAR_OFF = Q_BYTES + NSLOTS * GRAN_BYTES;
+  static constexpr int XCHG_OFF = BAR_OFF + 256;             // [2][2][128] row maxima, then [2][2][128] row sums
+  static constexpr int SMEM_BYTES = XCHG_OFF + 4096;         // base must be 1 KB aligned (checked)
+  static constexpr int TMEM_COLS = 512;
+  static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
+  static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(2 + 2 * NSLOTS + 10 + 1 <= 32, "barrier block");
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(AW_THREADS, 1)
+attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+                      const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                      __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items, int qtiles) {
+  using C = AttnWideCfg<NSPLIT>;
+  EB_DYN_SMEM_1K(smem);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
+  uint8_t* sQ = smem;
+  uint8_t* sRing = smem + C::Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* q_full = bars;                  // [1]
+  uint64_t* q_empty = bars + 1;             // [1]  last score tile of an item has been computed
+  uint64_t* kv_full = bars + 2;             // [NSLOTS]
+  uint64_t* kv_empty = kv_full + C::NSLOTS;
+  uint64_t* s_full = kv_empty + C::NSLOTS;  // [2]  S_g in TMEM
+  uint64_t* p_full = s_full + 2;            // [2]  P_g in TMEM (over S_g)
+  uint64_t* pv_done = p_full + 2;           // [2]  PV_g finished: O up to date (needed only for a rescale of O)
+  uint64_t* o_full = pv_done + 2;           // [2]  last PV of an item finished
+  uint64_t* o_empty = o_full + 2;           // [2]  epilogue has drained that O buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* xmax = reinterpret_cast<float*>(smem + C::XCHG_OFF);     // [2][2][128]
+  float* lsum = xmax + 512;                                        // [2][2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_items = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // grid <= num_items
+  const int my_tiles = my_items * AW_NT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmVh);
+    if (NSPLIT > 1) { tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmVl); }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_slot != 0) __trap();            // the whole TMEM was allocated: base is column 0 by construction
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    // ring order = MMA consumption order: K(0); then per global tile g: K(g+1), V(g).  Q is outside the ring.
+    if (lane == 0) {
+      uint32_t rc = 0;
+      auto item_coords = [&](int it, int& qt, int& h, int& b, int& bh) {
+        const int item = int(blockIdx.x) + it * int(gridDim.x);
+        qt = item % qtiles; bh = item / qtiles; h = bh % AW_HEADS; b = bh / AW_HEADS;
+      };
+      auto load_q = [&](int it) {
+        int qt, h, b, bh;
+        item_coords(it, qt, h, b, bh);
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, C::Q_BYTES);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_4d(sQ + kb * C::BLK, &tmQh, q_full, kb * 64, qt * AW_QT, h, b);
+          if (NSPLIT > 1) tma_load_4d(sQ + (2 + kb) * C::BLK, &tmQl, q_full, kb * 64, qt * AW_QT, h, b);
+        }
+      };
+      auto slot_acquire = [&](uint64_t*& full) -> uint8_t* {
+        const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
+        ++rc;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        full = &kv_full[slot];
+        mbar_expect_tx(full, C::GRAN_BYTES);
+        return sRing + slot * C::GRAN_BYTES;
+      };
+      auto load_k = [&](int g) {       // two granules: d blocks 0 and 1 of the 128-key tile (keys past 576 are zero-filled)
+        int qt, h, b, bh;
+        item_coords(g / AW_NT, qt, h, b, bh);
+        const int j = g % AW_NT;
+        for (int kb = 0; kb < 2; ++kb) {
+          uint64_t* full;
+          uint8_t* dst = slot_acquire(full);
+          tma_load_4d(dst, &tmQh, full, kb * 64, j * AW_KT, AW_HEADS + h, b);
+          if (NSPLIT > 1) tma_load_4d(dst + C::BLK, &tmQl, full, kb * 64, j * AW_KT, AW_HEADS + h, b);
+        }
+      };
+      auto load_v = [&](int g) {       // one granule per 64 keys of the tile
+        int qt, h, b, bh;
+        item_coords(g / AW_NT, qt, h, b, bh);
+        const int j = g % AW_NT;
+        const int ngran = j == AW_NT - 1 ? AW_LAST_KEYS / 64 : AW_KT / 64;
+        for (int kg = 0; kg < ngran; ++kg) {
+          uint64_t* full;
+          uint8_t* dst = slot_acquire(full);
+          tma_load_4d(dst, &tmVh, full, j * AW_KT + kg * 64, bh * AW_D, 0, 0);
+          if (NSPLIT > 1) tma_load_4d(dst + C::BLK, &tmVl, full, j * AW_KT + kg * 64, bh * AW_D, 0, 0);
+        }
+      };
+      if (my_tiles > 0) { load_q(0); load_k(0); }
+      for (int g = 0; g < my_tiles; ++g) {
+        if (g + 1 < my_tiles) {
+          if ((g + 1) % AW_NT == 0) load_q((g + 1) / AW_NT);
+          load_k(g + 1);
+        }
+        load_v(g);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (all lanes run the loop; the
+    // wrappers elect one lane).  Program order: S_0; { S_{g+1}; PV_g }.
+    constexpr uint32_t idesc_s = make_idesc_bf16(AW_QT, AW_KT);
+    constexpr uint32_t idesc_s_last = make_idesc_bf16(AW_QT, AW_LAST_KEYS);
+    constexpr uint32_t idesc_o = make_idesc_bf16(AW_QT, AW_D);
+    const uint32_t q_lo = sdesc_lo(smem_u32(sQ)), ring_lo = sdesc_lo(smem_u32(sRing));
+    uint32_t rc = 0;
+    auto slot_wait = [&](uint32_t& slot) -> uint32_t {
+      slot = rc % C::NSLOTS;
+      const uint32_t ph = (rc / C::NSLOTS) & 1;
+      ++rc;
+      mbar_wait(&kv_full[slot], ph);
+      return ring_lo + ((slot * C::GRAN_BYTES) >> 4);
+    };
+    auto issue_s = [&](int g) {
+      const int it = g / AW_NT, j = g % AW_NT;
+      const uint32_t d = C::T_S + uint32_t(g & 1) * 128u;
+      const uint32_t idesc = j == AW_NT - 1 ? idesc_s_last : idesc_s;
+      if (j == 0) mbar_wait(q_full, it & 1);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        uint32_t slot;
+        const uint32_t g_lo = slot_wait(slot);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t qh = sdesc_at(q_lo, kb * C::BLK + kk * 32);
+          const uint64_t kh = sdesc_at(g_lo, kk * 32);
+          umma_bf16<1>(d, qh, kh, idesc, (kb | kk) != 0 ? 1u : 0u);
+          if (NSPLIT > 1) {
+            const uint64_t ql = sdesc_at(q_lo, (2 + kb) * C::BLK + kk * 32);
+            const uint64_t kl = sdesc_at(g_lo, C::BLK + kk * 32);
+            umma_bf16<1>(d, qh, kl, idesc, 1u);
+            umma_bf16<1>(d, ql, kh, idesc, 1u);
+          }
+        }
+        umma_commit<1>(&kv_empty[slot]);
+      }
+      umma_commit<1>(&s_full[g & 1]);
+      if (j == AW_NT - 1) umma_commit<1>(q_empty);
+    };
+    auto issue_pv = [&](int g) {
+      const int it = g / AW_NT, j = g % AW_NT;
+      const uint32_t t_o = C::T_O + uint32_t(it & 1) * AW_D;
+      const uint32_t t_p = C::T_S + uint32_t(g & 1) * 128u;
+      if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue drained this O buffer (two items ago)
+      mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+      const int ngran = j == AW_NT - 1 ? AW_LAST_KEYS / 64 : AW_KT / 64;
+      for (int kg = 0; kg < ngran; ++kg) {
+        uint32_t slot;
+        const uint32_t g_lo = slot_wait(slot);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t vh = sdesc_at(g_lo, kk * 32);
+          const uint32_t pa = t_p + uint32_t(kg * 32 + kk * 8);      // 16 keys = 8 packed columns per k-step
+          umma_bf16_ts(t_o, pa, vh, idesc_o, (j == 0 && kg == 0 && kk == 0) ? 0u : 1u);
+          if (NSPLIT > 1) {
+            const uint64_t vl = sdesc_at(g_lo, C::BLK + kk * 32);
+            umma_bf16_ts(t_o, pa, vl, idesc_o, 1u);
+            umma_bf16_ts(t_o, pa + C::P_LO, vh, idesc_o, 1u);
+          }
+        }
+        umma_commit<1>(&kv_empty[slot]);
+      }
+      umma_commit<1>(&pv_done[g & 1]);
+      if (j == AW_NT - 1) umma_commit<1>(&o_full[it & 1]);
+    };
+    if (my_tiles > 0) issue_s(0);
+    for (int g = 0; g < my_tiles; ++g) {
+      if (g + 1 < my_tiles) issue_s(g + 1);
+      issue_pv(g);
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ softmax warps (8)
+    // Warps w and w+4 own the same TMEM lane quarter (query rows) and split the keys of a tile into two halves; the
+    // pair agrees on the row maximum through shared memory and a 64-thread named barrier -- which also separates the
+    // pair's loads of S from its stores of P into the same columns.
+    const int q = warp & 3;                       // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;               // key half handled by this warp
+    const int row = q * 32 + lane;                // query row inside the tile
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    const float c = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
+    float m_ref = 0.f, l = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < my_tiles; ++g) {
+      const int it = g / AW_NT, j = g % AW_NT;
+      const uint32_t sb = uint32_t(g & 1), par = uint32_t(g >> 1) & 1u;
+      const uint32_t t_s = C::T_S + sb * 128u + lane_sel;
+      const uint32_t t_o = C::T_O + uint32_t(it & 1) * AW_D + lane_sel;
+      const bool full_tile = j != AW_NT - 1;      // this warp: 64 keys of a full tile, 32 of the last one
+      const uint32_t col0 = full_tile ? hf * 64 : hf * 32;
+      if (j == 0) l = 0.f;
+      mbar_wait(&s_full[sb], par);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_s + col0, r0);
+      if (full_tile) tmem_ld32(t_s + col0 + 32, r1);
+      tmem_ld_wait();
+      float mt = __uint_as_float(r0[0]);
+#pragma unroll
+      for (int i = 1; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(r0[i]));
+      if (full_tile) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(r1[i]));
+      }
+      float* xm = xmax + (g & 1) * 256;
+      xm[hf * 128 + row] = mt;
+      tc_fence_before();
+      named_bar_sync<64>(1 + q);
+      tc_fence_after();
+      mt = fmaxf(mt, xm[(hf ^ 1) * 128 + row]);
+      if (j == 0) m_ref = mt;
+      const bool need = (j > 0) && ((mt - m_ref) * c > 8.0f);
+      float f = 1.0f;
+      if (need) { f = ex2_approx((m_ref - mt) * c); m_ref = mt; l *= f; }
+      const float mc = m_ref * c;
+      if (__any_sync(0xffffffffu, need)) {        // lazy rescale of this warp's 64 O columns: needs PV_{g-1} complete
+        mbar_wait(&pv_done[sb ^ 1], uint32_t((g - 1) >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(t_o + hf * 64 + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st32(t_o + hf * 64 + ch * 32, o);
+        }
+      }
+      // probabilities: 32 keys = 16 packed columns per chunk, written over S (hi at [0,64), lo at [64,128))
+      const uint32_t pcol0 = full_tile ? hf * 32 : hf * 16;
+      {
+        uint32_t hh[16], ll[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * e]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * e + 1]), c, -mc));
+          l += p0 + p1;
+          if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + pcol0, hh);
+        if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0, ll);
+      }
+      if (full_tile) {
+        uint32_t hh[16], ll[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r1[2 * e]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r1[2 * e + 1]), c, -mc));
+          l += p0 + p1;
+          if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + pcol0 + 16, hh);
+        if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0 + 16, ll);
+      }
+      tmem_st_wait();
+      if (j == AW_NT - 1) lsum[(it & 1) * 256 + hf * 128 + row] = l;   // for the epilogue warps, ordered by p_full
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (4): O / l -> ctx rows
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qt = item % qtiles, bh = item / qtiles;
+      const int h = bh % AW_HEADS, b = bh / AW_HEADS;
+      const int ob = it & 1;
+      mbar_wait(&o_full[ob], (it >> 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / (lsum[ob * 256 + row] + lsum[ob * 256 + 128 + row]);
+      const int tok = qt * AW_QT + row;
+      const long long orow = (long long)b * AW_TOK + tok;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(C::T_O + ob * AW_D + lane_sel + ch * 32, o);
+        tmem_ld_wait();
+        if (tok < AW_TOK) {
+          uint32_t hh[16], ll[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float v0 = __uint_as_float(o[2 * e]) * inv, v1 = __uint_as_float(o[2 * e + 1]) * inv;
+            if (NSPLIT > 1) split_pack2(v0, v1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(v0, v1);
+          }
+          const long long off = orow * (AW_HEADS * AW_D) + h * AW_D + ch * 32;
+          uint4* oh = reinterpret_cast<uint4*>(ctx_hi + off);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = make_uint4(hh[4 * e], hh[4 * e + 1], hh[4 * e + 2], hh[4 * e + 3]);
+          if (NSPLIT > 1) {
+            uint4* ol = reinterpret_cast<uint4*>(ctx_lo + off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ol[e] = make_uint4(ll[4 * e], ll[4 * e + 1], ll[4 * e + 2], ll[4 * e + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(0u, C::TMEM_COLS);
+}
+
+template <int NSPLIT>
+static int launch_attention_wide(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int qtiles,
+                                 cudaStream_t stream) {
+  using C = AttnWideCfg<NSPLIT>;
+  auto kern = attention_wide_kernel<NSPLIT>;
+  static bool attr_done[64] = {false};
+  const int dev_ = current_device();
+  if (!attr_done[dev_]) {
+    EB_CUDA(EB_SET_MAX_SMEM(kern, C::SMEM_BYTES));
+    attr_done[dev_] = true;
+  }
+  const int items = B * AW_HEADS * qtiles;
+  const int grid = items < num_sms() ? items : num_sms();
+  ProfScope prof("attention_wide_kernel", stream);
+  EB_LAUNCH_SMEM(kern, grid, AW_THREADS, C::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3], ctx_hi, ctx_lo, items, qtiles);
+  EB_CHECK_LAUNCH("attention_wide_kernel");
+  return 0;
+}
+
+// same operands and meaning as attention_run (attention.cu)
+int attention_wide_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
+                       const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
+                       int query_rows, cudaStream_t stream) {
+  EB_REQUIRE(query_rows > 0 && query_rows <= AW_TOK, "attention: query_rows must be in (0, 576]");
+  const int qtiles = (query_rows + AW_QT - 1) / AW_QT;
+  EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");
+  EB_REQUIRE(nsplit == 1 || (qk_lo && vt_lo && ctx_lo), "attention: bf16x3 mode needs the lo parts");
+  CUtensorMap tm[4];
+  int rc;
+  const long long fs = (long long)AW_TOK * 2 * AW_HEADS * AW_D;  // frame stride of the qk buffer
+  for (int part = 0; part < (nsplit == 3 ? 2 : 1); ++part) {
+    const __nv_bfloat16* qk = part == 0 ? qk_hi : qk_lo;
+    const __nv_bfloat16* vt = part == 0 ? vt_hi : vt_lo;
+    // Q and K tiles are both 128 rows x 64 of the [Q | K] buffer: one map, the K tiles at head coordinate 8 + h
+    if ((rc = make_operand_tmap(&tm[0 + part], qk, AW_D, AW_TOK, 2 * AW_HEADS * AW_D, 2 * AW_HEADS, AW_D, B, fs, 128)))
+      return rc;
+    if ((rc = make_operand_tmap(&tm[2 + part], vt, AW_TOK, (long long)B * AW_HEADS * AW_D, AW_TOK, 1, 0, 1, 0, AW_D)))
+      return rc;
+  }
+  if (nsplit == 1) { tm[1] = tm[0]; tm[3] = tm[2]; }
+  return nsplit == 3 ? launch_attention_wide<3>(tm, ctx_hi, ctx_lo, B, qtiles, stream)
+                     : launch_attention_wide<1>(tm, ctx_hi, ctx_lo, B, qtiles, stream);
+}
+
+}  // namespace eb

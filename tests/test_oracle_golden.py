@@ -19,9 +19,11 @@ def test_oracle_matches_reference_golden(preset, kind, state_dicts):
     wseed, iseed, batch = (int(v) for v in gold["meta"])
     assert wseed == 5
     x = synthetic_heatmaps(preset, batch, seed=iseed, kind=kind)
-    # the regenerated input is the one the golden was made from
+    # the regenerated input is the one the golden was made from.  The seeded integers / uniforms are identical on every
+    # host; torch's fp32 exp / cos / sin may differ in the last ulp between SIMD paths (observed 1e-9 relative on the
+    # checksums between two build hosts), which the output tolerances below absorb.
     np.testing.assert_allclose([x.double().sum().item(), x.double().pow(2).sum().item()],
-                               gold["input_checksum"], rtol=1e-12)
+                               gold["input_checksum"], rtol=1e-7)
     taps = {}
     with torch.no_grad():
         pose = orc.forward(state_dicts(preset), x, preset, taps=taps)

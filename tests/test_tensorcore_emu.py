@@ -182,10 +182,28 @@ def test_gemm_grouped_operands(be, variant, prec):
 
 
 @pytest.mark.parametrize("prec", [1, 0])
-def test_fused_attention_kernel(be, prec):
+@pytest.mark.parametrize("variant", ["", "wide"])
+def test_fused_attention_kernel(be, prec, variant):
     """14 warps, ten mbarrier families, S and O double-buffered in tensor memory, P as the TS-form A operand, lazy rescale;
-    2 frames = 80 work items on the emulated 6-SM device, i.e. ~13 items per persistent CTA (phase parities wrap)"""
+    2 frames = 80 work items on the emulated 6-SM device, i.e. ~13 items per persistent CTA (phase parities wrap).
+    variant 'wide' (EGOTAP_ATTN=wide, csrc/attention_wide.cu): 128-key score tiles with a 64-key tail, P written over S,
+    one software pipeline across the work items of a CTA (odd tile count per item: buffers alternate between items)"""
     emu, orc = be
+    old_env = os.environ.get("EGOTAP_ATTN")
+    try:
+        if variant:
+            os.environ["EGOTAP_ATTN"] = variant
+        else:
+            os.environ.pop("EGOTAP_ATTN", None)
+        _fused_attention_case(emu, orc, prec)
+    finally:
+        if old_env is None:
+            os.environ.pop("EGOTAP_ATTN", None)
+        else:
+            os.environ["EGOTAP_ATTN"] = old_env
+
+
+def _fused_attention_case(emu, orc, prec):
     torch.manual_seed(30 + prec)
     frames = 2
     qk = torch.randn(frames * 576, 2048) * 1.5
@@ -297,7 +315,7 @@ def test_persistent_chain_kernel(frames, J, x3):
 
 @pytest.mark.parametrize("preset,env", [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
                                         ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
-                                        ("EgoCap", {"EGOTAP_SPLITK": "1"})])
+                                        ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"})])
 def test_whole_inference_path_on_product_source(preset, env, state_dicts):
     """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
     from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
@@ -497,8 +515,10 @@ def test_tensor_core_kernels_do_not_depend_on_the_thread_schedule(be, mode):
         test_gemm_tile_configurations(be, 0, 1)
         test_gemm_tile_configurations(be, 3, 0)
         test_gemm_epilogue_modes(be, 4, 1)
-        test_fused_attention_kernel(be, 0)
-        test_fused_attention_kernel(be, 1)
+        test_fused_attention_kernel(be, 0, "")
+        test_fused_attention_kernel(be, 1, "")
+        test_fused_attention_kernel(be, 0, "wide")
+        test_fused_attention_kernel(be, 1, "wide")
         test_persistent_chain_kernel(5, 15, True)
         test_persistent_bptt_kernel(be, 5, 15, True)
         test_persistent_bptt_kernel(be, 150, 17, False)
