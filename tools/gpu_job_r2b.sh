@@ -1,0 +1,31 @@
+#!/bin/bash
+# Round-2 inference A/B job: first hardware run of the opt-in variants written after round 1's GPU budget was spent.
+#   gpurun --timeout 1200 -- 'bash tools/gpu_job_r2b.sh > gpurun_out/r2b.log 2>&1'
+# 1. parity of the wide attention kernel (EGOTAP_ATTN=wide) op-level and through the whole path (subprocess per case)
+# 2. the attention op alone, v1 vs wide, both precisions (CUDA events)           -> is 128-key tiling faster?
+# 3. bench lines of the default workload with / without it, both precisions       -> step-level effect
+# 4. small-batch latency: batch 1 / 8 / 32 with and without EGOTAP_SPLITK=1
+# 5. one ncu --set full capture of the wide attention kernel (tensor-pipe active %, issue stalls of the MMA warp)
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv
+timeout 900 python -m pytest tests/test_zzz_attention_wide_gpu.py -m gpu -q 2>&1 | tail -15
+cat gpurun_out/attention_wide.jsonl
+for prec in bf16x3 bf16; do
+  for v in v1 wide; do
+    if [ $v = wide ]; then export EGOTAP_ATTN=wide; else unset EGOTAP_ATTN; fi
+    echo "variant $v"; timeout 300 python tools/attn_only.py 256 $prec 2>&1 | tail -1
+  done
+done
+unset EGOTAP_ATTN
+for prec in bf16x3 bf16; do
+  timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_v1.json 2>&1 | tail -1 | cut -c1-700
+  EGOTAP_ATTN=wide timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_wide.json 2>&1 | tail -1 | cut -c1-700
+done
+for b in 1 8 32; do
+  timeout 300 python bench.py --batch $b --steps 50 --warmup 5 2>&1 | tail -1 | cut -c1-260
+  EGOTAP_SPLITK=1 timeout 300 python bench.py --batch $b --steps 50 --warmup 5 2>&1 | tail -1 | cut -c1-260
+done
+EGOTAP_ATTN=wide timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_wide -c 2 \
+    -o gpurun_out/r2b_attention_wide python tools/attn_only.py 64 bf16x3 > gpurun_out/r2b_ncu_attn.log 2>&1
+tail -3 gpurun_out/r2b_ncu_attn.log | cut -c1-300
