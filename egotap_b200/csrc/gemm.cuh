@@ -156,7 +156,92 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row,
   }
 }
 
-template <int CG, int BN, int NSPLIT, int STAGES>
+// ---- coalesced variant of the epilogue (COAL = true; opt-in EGOTAP_EPI=coalesced) ---------------------------------
+// tcgen05.ld hands every thread one ROW of the tile (32 consecutive columns), so the row-strided stores / residual loads
+// above touch 32 different 128-byte lines per warp instruction: on the K = 1024 GEMMs (out-projection 607 vs MLP-down
+// 1346 TFLOP/s in bf16 mode, profiles/r01c) the epilogue is bound by LSU wavefronts, not by HBM.  Here the 32 x 32 chunk
+// of a warp goes through a 4 KB shared-memory staging block (16-byte chunks XOR-swizzled by row, conflict-free per
+// quarter warp both ways) and comes back with lane l holding the 16-byte segment l % 8 of rows 4 i + l / 8: every global
+// access of the warp then covers 4 full 128-byte lines (fp32) or 4 x 64 contiguous bytes (bf16 hi / lo).  The pointwise
+// part runs in the row domain, the residual add and the stores in the transposed domain; results are identical.
+struct EpiRowsT {            // transposed-domain addressing of the 8 rows a lane touches, fixed per tile
+  int orow[8], rrow[8];      // output / residual row of tile row 4 i + lane / 8 (row counts stay far below 2^31)
+  int cs[8];                 // column shift of that row (STORE_JOINT_REGROUP / STORE_HEAD_MERGE)
+  unsigned ok;               // bit i: the row exists
+};
+__device__ __forceinline__ EpiRowsT epi_rows_t(const EpiRow& row, bool row_ok, int lane) {
+  EpiRowsT t;
+  t.ok = 0u;
+  const int sub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + sub;
+    t.orow[i] = __shfl_sync(0xffffffffu, int(row.orow), rr);
+    t.rrow[i] = __shfl_sync(0xffffffffu, int(row.rrow), rr);
+    t.cs[i] = __shfl_sync(0xffffffffu, row.col_shift, rr);
+    t.ok |= unsigned(__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr)) << i;
+  }
+  return t;
+}
+__device__ __forceinline__ void epi_load_resid_t(const EpiParams& p, const EpiRowsT& rows, int n0, int lane, float4 (&t)[8]) {
+  const int c0 = n0 + p.col_off + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if ((rows.ok >> i) & 1u) t[i] = *reinterpret_cast<const float4*>(p.resid + (long long)rows.rrow[i] * p.resid_ld + c0 + rows.cs[i]);
+}
+__device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const EpiRowsT& rows, int n0, uint32_t (&r)[32],
+                                                    const float4 (&t)[8], float4* stg, int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (p.scale) {
+    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 s = __ldg(s4 + j);
+      v[4 * j] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
+    }
+  }
+  if (p.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int seg = lane & 7, sub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + sub;
+    float4 x = stg[rr * 8 + (seg ^ (rr & 7))];
+    if ((rows.ok >> i) & 1u) {
+      if (p.resid) { x.x += t[i].x; x.y += t[i].y; x.z += t[i].z; x.w += t[i].w; }
+      const long long o = (long long)rows.orow[i] * p.ldo + n0 + p.col_off + rows.cs[i] + seg * 4;
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+      if (p.out_hi) {
+        uint32_t h0, l0, h1, l1;
+        split_pack2(x.x, x.y, h0, l0);
+        split_pack2(x.z, x.w, h1, l1);
+        *reinterpret_cast<uint2*>(p.out_hi + o) = make_uint2(h0, h1);
+        if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + o) = make_uint2(l0, l1);
+      }
+    }
+  }
+  __syncwarp();                 // the staging block is rewritten by the next chunk
+}
+
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false>
 struct GemmCfg {
   static constexpr int BM = 128;                     // rows per CTA (tile rows = BM * CG)
   static constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
@@ -166,21 +251,22 @@ struct GemmCfg {
   static constexpr int B_BYTES = BNL * BK * 2;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
   static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+  static constexpr int STG_BYTES = COAL ? EPI_WARPS * 4096 : 0;   // coalesced epilogue: one 32 x 32 fp32 block per warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // + alignment slack
   static constexpr int COLS_PER_EPI_GROUP = BN / (EPI_WARPS / 4);
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int CG, int BN, int NSPLIT, int STAGES>
-__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES>::THREADS), 1)
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
-  using C = GemmCfg<CG, BN, NSPLIT, STAGES>;
+  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL>;
   EB_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -307,6 +393,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const EpiRow row = epi_row(ep, g, row_ok ? m : 0, s.N);
       float4 t_cur[8], t_nxt[8];
       const int n_first = n_blk * BN + col_base;
+      if constexpr (COAL) {
+        // transposed-domain epilogue (see epi_apply_coalesced); the transposed V store of STORE_QKV keeps the row-domain path
+        float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES) + (warp - 2) * 256;
+        const EpiRowsT rows = epi_rows_t(row, row_ok, lane);
+#pragma unroll 1
+        for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
+          const int n0 = n_first + c * 32;
+          if (n0 >= s.N) break;
+          const bool v_part = ep.store == STORE_QKV && n0 >= ep.qk_cols;
+          uint32_t r[32];
+          tmem_ld32(t_addr + col_base + c * 32, r);
+          // coalesced residual loads of this chunk, in flight across the TMEM wait, the pointwise math and the staging
+          if (ep.resid != nullptr && !v_part) epi_load_resid_t(ep, rows, n0, lane, t_cur);
+          tmem_ld_wait();
+          if (v_part) {
+            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur);
+          } else {
+            epi_apply_coalesced(ep, rows, n0, r, t_cur, stg, lane);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+        }
+        continue;
+      }
       if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur);
 #pragma unroll 1
       for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {

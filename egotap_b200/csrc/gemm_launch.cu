@@ -3,14 +3,16 @@
 #include "host_util.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace eb {
 
-template <int CG, int BN, int NS, int ST>
+template <int CG, int BN, int NS, int ST, bool COAL = false>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
-  using C = GemmCfg<CG, BN, NS, ST>;
-  auto kern = gemm_tc_kernel<CG, BN, NS, ST>;
+  using C = GemmCfg<CG, BN, NS, ST, COAL>;
+  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL>;
   // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
@@ -33,15 +35,16 @@ struct Variant {
   const char* name;
   int cg, bn, nsplit;
   int (*launch)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);
+  int (*launch_coalesced)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);   // EGOTAP_EPI=coalesced
 };
 
 static const Variant kVariants[] = {
-    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>},
-    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>},
-    {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>},
-    {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>},
-    {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>},
-    {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>},
+    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>},
+    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>},
+    {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>, &launch_variant<1, 256, 1, 4, true>},
+    {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>, &launch_variant<1, 256, 3, 2, true>},
+    {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>, &launch_variant<2, 256, 1, 6, true>},
+    {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>, &launch_variant<2, 256, 3, 3, true>},
 };
 static const int kNumVariants = int(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -95,6 +98,10 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
   GemmShape sh = s;
   if (sh.gdiv <= 0) sh.gdiv = int(a.g0_count > 0 ? a.g0_count : 1);
   ProfScope prof("gemm_tc_kernel", stream, s.M, s.N, s.K, s.groups, variant);
+  // EGOTAP_EPI=coalesced (opt-in, A/B): the epilogue that re-distributes each warp's chunk through shared memory so that
+  // its global accesses are coalesced (gemm.cuh); read per call so that one process can compare the two
+  const char* epi_env = getenv("EGOTAP_EPI");
+  if (epi_env && strcmp(epi_env, "coalesced") == 0) return v.launch_coalesced(tm, sh, ep, stream);
   return v.launch(tm, sh, ep, stream);
 }
 

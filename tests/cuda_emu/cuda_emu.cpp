@@ -190,6 +190,16 @@ double shfl_xor(double v, int lane_mask) {
   return r;
 }
 
+double shfl_idx(double v, int src_lane) {
+  need_coop("warp shuffle");
+  Cta& c = C();
+  c.warp_buf[cur->warp][cur->lane] = v;
+  warp_barrier();
+  const double r = c.warp_buf[cur->warp][src_lane & 31];
+  warp_barrier();
+  return r;
+}
+
 bool any_sync(bool pred) {
   need_coop("warp vote");
   Cta& c = C();

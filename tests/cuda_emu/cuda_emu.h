@@ -39,6 +39,12 @@ void named_barrier(int id, int nthreads);
 void cluster_sync();
 double shfl_xor(double v, int lane_mask);
 inline float shfl_xor(float v, int lane_mask) { return float(shfl_xor(double(v), lane_mask)); }   // exact round trip
+double shfl_idx(double v, int src_lane);
+inline int shfl_idx(int v, int src_lane) { return int(shfl_idx(double(v), src_lane)); }
+inline long long shfl_idx(long long v, int src_lane) {       // exact for |v| < 2^53 (row / element offsets)
+  if (v > (1ll << 53) || v < -(1ll << 53)) { fprintf(stderr, "cuda_emu: 64-bit shuffle value out of the exact range\n"); abort(); }
+  return (long long)shfl_idx(double(v), src_lane);
+}
 bool any_sync(bool pred);
 void wait_phase(const void* mbar_first_word, unsigned parity);   // block until the mbarrier phase bit != parity
 void yield_wait();              // a spinning wait gives the other fibers a turn (and feeds the deadlock detector)
@@ -66,6 +72,7 @@ int num_sms();
 #define __syncthreads() eb_emu::syncthreads()
 #define __syncwarp() eb_emu::syncwarp()
 #define __shfl_xor_sync(mask, v, o) eb_emu::shfl_xor((v), (o))
+#define __shfl_sync(mask, v, src) eb_emu::shfl_idx((v), (src))
 #define __any_sync(mask, p) eb_emu::any_sync(p)
 #define __trap() (fprintf(stderr, "cuda_emu: __trap() at %s:%d\n", __FILE__, __LINE__), abort())
 #define __ldg(p) (*(p))
