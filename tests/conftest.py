@@ -18,7 +18,7 @@ def pytest_configure(config):
 # were brought up on the CPU emulation after the round's GPU budget was spent (first hardware run = the round-end tier).
 # With -x a failure among the latter must not hide the parity tests of the path BASELINE.json names.
 _GPU_FILE_ORDER = ["test_gemm_gpu.py", "test_ops_gpu.py", "test_lifting_gpu.py", "test_metrics.py", "test_heatmap_net.py",
-                   "test_gt_heatmaps.py", "test_train_kernels.py", "test_zz_train_gpu.py", "test_zzz_attention_wide_gpu.py"]
+                   "test_gt_heatmaps.py", "test_train_kernels.py", "test_zz_train_gpu.py", "test_zzz_attention_wide_gpu.py", "test_zzz_epilogue_coalesced_gpu.py"]
 
 
 def pytest_collection_modifyitems(config, items):

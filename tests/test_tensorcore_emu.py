@@ -121,6 +121,57 @@ def test_gemm_epilogue_modes(be, variant, prec):
     _close(e1["out_f32"], e2["out_f32"], tol)
 
 
+class _env:
+    """set / unset one environment switch for the duration of a block (the library reads these two per call)"""
+
+    def __init__(self, key, value):
+        self.key, self.value = key, value
+
+    def __enter__(self):
+        self.old = os.environ.get(self.key)
+        if self.value:
+            os.environ[self.key] = self.value
+        else:
+            os.environ.pop(self.key, None)
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop(self.key, None)
+        else:
+            os.environ[self.key] = self.old
+
+
+def test_coalesced_epilogue_variant(be):
+    """EGOTAP_EPI=coalesced (csrc/gemm.cuh, COAL = true): every epilogue / store mode, a paired-SM configuration, ragged M,
+    grouped operands with head-merged stores -- against the oracle, and bit-for-bit against the default epilogue (the
+    arithmetic is the same; g++ makes the same contraction choices in both code paths)"""
+    emu, _ = be
+    with _env("EGOTAP_EPI", "coalesced"):
+        for variant, prec in VARIANTS:
+            test_gemm_tile_configurations(be, variant, prec)
+        test_gemm_epilogue_modes(be, 1, 0)
+        test_gemm_epilogue_modes(be, 4, 1)
+        test_gemm_epilogue_modes(be, 5, 0)
+        test_gemm_grouped_operands(be, 1, 0)
+        test_gemm_grouped_operands(be, 0, 1)
+    torch.manual_seed(77)
+    M, N, K = 300, 512, 128
+    a, b = torch.randn(M, K), torch.randn(N, K)
+    ah, al = _pairs(a)
+    bh, bl = _pairs(b)
+    bias, h0 = torch.randn(N), torch.randn(M, N)
+    outs = []
+    for mode in ("", "coalesced"):
+        h = h0.clone()
+        hi, lo = torch.full((M, N), float("nan"), dtype=BF16), torch.full((M, N), float("nan"), dtype=BF16)
+        with _env("EGOTAP_EPI", mode):
+            emu.gemm_tc(ah, al, bh, bl, M, N, K, precision=0, variant=5, bias=bias, act=1, resid=h, resid_ld=N, out_f32=h, out_hi=hi,
+                        out_lo=lo, ldo=N)
+        outs.append((h, hi, lo))
+    for x, y in zip(outs[0], outs[1]):
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("variant,prec", [(1, 0), (0, 1)])
 def test_gemm_grouped_operands(be, variant, prec):
     """the group layouts the path uses: per-(frame, head) attention-style operands with head-merged output, and the
@@ -189,18 +240,8 @@ def test_fused_attention_kernel(be, prec, variant):
     variant 'wide' (EGOTAP_ATTN=wide, csrc/attention_wide.cu): 128-key score tiles with a 64-key tail, P written over S,
     one software pipeline across the work items of a CTA (odd tile count per item: buffers alternate between items)"""
     emu, orc = be
-    old_env = os.environ.get("EGOTAP_ATTN")
-    try:
-        if variant:
-            os.environ["EGOTAP_ATTN"] = variant
-        else:
-            os.environ.pop("EGOTAP_ATTN", None)
+    with _env("EGOTAP_ATTN", variant):
         _fused_attention_case(emu, orc, prec)
-    finally:
-        if old_env is None:
-            os.environ.pop("EGOTAP_ATTN", None)
-        else:
-            os.environ["EGOTAP_ATTN"] = old_env
 
 
 def _fused_attention_case(emu, orc, prec):

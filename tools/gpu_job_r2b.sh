@@ -6,11 +6,14 @@
 # 3. bench lines of the default workload with / without it, both precisions       -> step-level effect
 # 4. small-batch latency: batch 1 / 8 / 32 with and without EGOTAP_SPLITK=1
 # 5. one ncu --set full capture of the wide attention kernel (tensor-pipe active %, issue stalls of the MMA warp)
+# 6. the coalesced GEMM epilogue (EGOTAP_EPI=coalesced): parity, then bench lines with it alone and with both switches
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv
 timeout 900 python -m pytest tests/test_zzz_attention_wide_gpu.py -m gpu -q 2>&1 | tail -15
 cat gpurun_out/attention_wide.jsonl
+timeout 1500 python -m pytest tests/test_zzz_epilogue_coalesced_gpu.py -m gpu -q 2>&1 | tail -15
+cat gpurun_out/epilogue_coalesced.jsonl
 for prec in bf16x3 bf16; do
   for v in v1 wide; do
     if [ $v = wide ]; then export EGOTAP_ATTN=wide; else unset EGOTAP_ATTN; fi
@@ -21,7 +24,10 @@ unset EGOTAP_ATTN
 for prec in bf16x3 bf16; do
   timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_v1.json 2>&1 | tail -1 | cut -c1-700
   EGOTAP_ATTN=wide timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_wide.json 2>&1 | tail -1 | cut -c1-700
+  EGOTAP_EPI=coalesced timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_coal.json 2>&1 | tail -1 | cut -c1-700
+  EGOTAP_EPI=coalesced EGOTAP_ATTN=wide timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_both.json 2>&1 | tail -1 | cut -c1-700
 done
+for f in gpurun_out/r2b_bench_*.json; do echo $f; python tools/summarize_bench.py $f | head -12; done
 for b in 1 8 32; do
   timeout 300 python bench.py --batch $b --steps 50 --warmup 5 2>&1 | tail -1 | cut -c1-260
   EGOTAP_SPLITK=1 timeout 300 python bench.py --batch $b --steps 50 --warmup 5 2>&1 | tail -1 | cut -c1-260
