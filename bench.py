@@ -334,6 +334,16 @@ def run_ours(args):
             t = max(ts) if name == "layernorm1024_kernel" else ts[0]   # full-size LN launches (the last one is compacted)
             hbm[name] = dict(ms=t, bytes=nbytes, achieved_gbs=nbytes / t / 1e6, peak_gbs=pk["hbm_gbs"],
                              frac=nbytes / t / 1e6 / pk["hbm_gbs"])
+    # fused attention (second-largest kernel family): algorithmic 4*T*T*d FLOP per (frame, head) over the query rows each
+    # layer needs (all 576 in layers 0-1, the live tokens in the last one), CUDA-event durations of the same step
+    att = [r["ms"] for r in all_recs if r["name"].startswith("attention")]
+    attention = None
+    if att:
+        att_flops = 4.0 * 128 * 576 * (576 + 576 + 2 * J * 16) * 8 * B
+        att_tf = att_flops / (sum(att) * 1e-3) / 1e12
+        attention = dict(kernel=sorted({r["name"] for r in all_recs if r["name"].startswith("attention")})[0], launches=len(att),
+                         ms=sum(att), achieved=att_tf, peak=pk["bf16_sustained"], unit="TFLOP/s", frac=att_tf / pk["bf16_sustained"],
+                         mma_frac=att_tf * nsplit / pk["bf16_sustained"], share_of_step=sum(att) / (ms / K))
     fps = total * K / (ms * 1e-3)
     flop_frame = FLOP_PER_FRAME[args.preset] + (107.41e9 if est is not None else 0.0)   # + producers
     whole = dict(achieved=fps / world * flop_frame / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s")
@@ -350,7 +360,7 @@ def run_ours(args):
                 e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, checked=e2e_ok),
                 gpu_launches=int(launches), clocks=clocks.summary(), roofline=roofline, roofline_whole_step=whole,
-                roofline_hbm_kernels=hbm,
+                roofline_hbm_kernels=hbm, roofline_attention=attention,
                 cpu_baseline=(dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
                                    sample="3 steps x batch %d frames of the same workload, fp32 oracle" % cpu["batch"])
                               if cpu else None),

@@ -280,6 +280,8 @@ def test_whole_training_step_on_product_kernel_source():
     """forward + loss + backward with EVERY launch -- tcgen05 GEMMs (all operand / group / epilogue patterns of the
     engine), fused attention, and all bandwidth kernels -- executed from the product's own kernel source on the
     emulation, fp32-parity operand mode, against torch.autograd on the restated forward"""
+    if _heavy_in_parent("test_whole_training_step_on_product_kernel_source"):
+        return
     emu, _ = build_emu.make_backend(real_tensor_core=True)
     preset, batch = "UnrealEgo", 1
     sd = weights.make_state_dict(preset, seed=5)
@@ -354,17 +356,10 @@ def test_persistent_chain_kernel(frames, J, x3):
     assert (out.double() - ref).abs().max().item() < (2e-5 if x3 else 2e-3)
 
 
-@pytest.mark.parametrize("preset,env", [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
-                                        ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
-                                        ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"})])
-def test_whole_inference_path_on_product_source(preset, env, state_dicts):
-    """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
-    from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
-    attention, persistent chain, last-layer dummy-row skipping), the A/B switches, and the opt-in small-batch split-K of
-    the first FC block.  Runs in a subprocess because the
-    switches are read from the environment once per process."""
-    import json
-    code = r'''
+_INFER_CASES = [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
+                ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
+                ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"})]
+_INFER_CODE = r'''
 import ctypes as C, json, os, sys
 sys.path[:0] = %r
 import torch, build_emu, egotap_oracle as orc, weights
@@ -395,13 +390,82 @@ assert lib.egotap_b200_forward(plan, x.data_ptr(), 1, pose.data_ptr(), -1, None)
 with torch.no_grad():
     ref = orc.forward(sd, x, preset)
 print("RESULT " + json.dumps(orc.parity_report(pose, ref)))
-''' % ([os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
-        os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu")], preset)
-    e = dict(os.environ)
-    e.update(env)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=1500)
-    assert r.returncode == 0, r.stderr[-1500:]
-    rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+'''
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CHILD_PATHS = [_ROOT, os.path.join(_ROOT, "oracle"), os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu")]
+# The subprocess cases of this file and its two longest in-process tests are started in the background as soon as the first
+# test of the module runs and are collected by the tests that own them, so they overlap with the in-process tests
+# (the suite is CPU-only and the emulation is single-threaded).  EGOTAP_EMU_CHILD marks a child pytest.
+_BG = {}
+_HEAVY = ["test_whole_training_step_on_product_kernel_source", "test_engine_with_persistent_bptt_matches_per_joint_path"]
+
+
+def _in_child():
+    return os.environ.get("EGOTAP_EMU_CHILD") == "1"
+
+
+def _spawn(key, cmd, env):
+    import tempfile
+    out = tempfile.TemporaryFile(mode="w+")
+    _BG[key] = (subprocess.Popen(cmd, stdout=out, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, **env), cwd=_ROOT), out)
+
+
+def _collect(key, timeout=2400):
+    proc, out = _BG.pop(key)
+    try:
+        proc.wait(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+        raise
+    out.seek(0)
+    text = out.read()
+    out.close()
+    return proc.returncode, text
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _background_children(request):
+    if not _in_child():
+        selected = {item.name for item in request.session.items if os.path.basename(str(item.fspath)) == os.path.basename(__file__)}
+        build_emu.build()                       # once, before any child could race to build it
+        for i, (preset, env) in enumerate(_INFER_CASES):
+            if any(n.startswith("test_whole_inference_path_on_product_source[") and n.endswith("env%d]" % i) for n in selected):
+                _spawn(("infer", i), [sys.executable, "-c", _INFER_CODE % (_CHILD_PATHS, preset)], env)
+        for name in _HEAVY:
+            if name in selected:
+                _spawn(("heavy", name), [sys.executable, "-m", "pytest", "%s::%s" % (os.path.abspath(__file__), name), "-x", "-q",
+                                         "-p", "no:cacheprovider"], {"EGOTAP_EMU_CHILD": "1"})
+    yield
+    for proc, out in _BG.values():
+        if proc.poll() is None:
+            proc.kill()
+        out.close()
+    _BG.clear()
+
+
+def _heavy_in_parent(name):
+    """True (after asserting on the child's result) when the calling test ran in a background child"""
+    if _in_child() or ("heavy", name) not in _BG:
+        return False
+    rc, text = _collect(("heavy", name))
+    assert rc == 0, text[-3000:]
+    return True
+
+
+@pytest.mark.parametrize("preset,env", _INFER_CASES)
+def test_whole_inference_path_on_product_source(preset, env, state_dicts):
+    """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
+    from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
+    attention, persistent chain, last-layer dummy-row skipping), the A/B switches, the opt-in small-batch split-K of
+    the first FC block and the opt-in wide attention kernel.  Runs in a subprocess because most
+    switches are read from the environment once per process."""
+    import json
+    key = ("infer", _INFER_CASES.index((preset, env)))
+    if key not in _BG:
+        _spawn(key, [sys.executable, "-c", _INFER_CODE % (_CHILD_PATHS, preset)], env)
+    rc, text = _collect(key, timeout=1500)
+    assert rc == 0, text[-1500:]
+    rep = json.loads([l for l in text.splitlines() if l.startswith("RESULT ")][0][7:])
     assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep       # the GPU parity tests' own bounds
 
 
@@ -599,6 +663,8 @@ def test_persistent_bptt_kernel(be, frames, J, x3):
 
 def test_engine_with_persistent_bptt_matches_per_joint_path():
     """the training engine with persistent_bptt: same gradients as with the per-joint backward (everything else equal)"""
+    if _heavy_in_parent("test_engine_with_persistent_bptt_matches_per_joint_path"):
+        return
     lib = _emu_lib()
     lib.emu_set_num_sms(32)
     try:
