@@ -37,7 +37,6 @@ __device__ unsigned long long g_attn_trace[32];
 
 constexpr int AT_TOK = 576, AT_HEADS = 8, AT_D = 128, AT_QT = 128, AT_KT = 64;
 constexpr int AT_NT = AT_TOK / AT_KT;                        // 9 key tiles
-constexpr int AT_QTILES = (AT_TOK + AT_QT - 1) / AT_QT;      // 5 query tiles (the last one is half empty)
 constexpr int AT_THREADS = 64 + 256 + 128;                   // TMA + MMA warps, 8 softmax warps, 4 epilogue warps
 
 template <int NSPLIT>

@@ -18,11 +18,6 @@ int reduce_partials_run(const float*, int, long long, float*, cudaStream_t);
 namespace {
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 __device__ __forceinline__ void st_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long off, float4 v) {
   uint32_t h0, h1, l0, l1;
   split_pack2(v.x, v.y, h0, l0);

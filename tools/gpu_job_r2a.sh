@@ -6,6 +6,7 @@
 # 3. first bench lines of config 5 (bf16 and parity mode, batch 32 = the reference's, and 256) with per-kernel tables
 # 4. launch list of one training step under ncu (shares only)
 set -x
+export EGOTAP_STRICT_UNVERIFIED=1      # the quarantined first-hardware-run tests (tests/conftest.py) run as ordinary tests here
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv
 timeout 900 python -m pytest tests/test_train_kernels.py tests/test_gt_heatmaps.py -m gpu -q -x 2>&1 | tail -15

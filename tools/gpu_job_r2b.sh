@@ -8,6 +8,7 @@
 # 5. one ncu --set full capture of the wide attention kernel (tensor-pipe active %, issue stalls of the MMA warp)
 # 6. the coalesced GEMM epilogue (EGOTAP_EPI=coalesced): parity, then bench lines with it alone and with both switches
 set -x
+export EGOTAP_STRICT_UNVERIFIED=1      # the quarantined first-hardware-run tests (tests/conftest.py) run as ordinary tests here
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv
 timeout 900 python -m pytest tests/test_zzz_attention_wide_gpu.py -m gpu -q 2>&1 | tail -15
