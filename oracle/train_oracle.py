@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracle of the pose-estimator TRAINING STEP (SURVEY.md section 8(f) row f2,
-BASELINE config 5).  Groundwork for the next round: there is no CUDA training path yet.
+BASELINE config 5): the checker of the CUDA training path (egotap_b200/training.py, csrc/train_*.cu).
 
 Restates, in fp32/fp64 torch on the CPU:
   * the train-mode forward: identical to the eval forward except that the six FC blocks use BatchNorm1d batch
