@@ -180,8 +180,8 @@ def run_ours(args):
 
     B, K, W = args.batch, args.steps, args.warmup
     torch.manual_seed(0)                                   # reference-style random init (kaiming), same on every rank
-    net = egotap_b200.EgoTAPAutoEncoder(make_opt(args.preset, b200_precision=args.precision, b200_max_batch=B),
-                                        input_channel_scale=2)
+    net = egotap_b200.EgoTAPAutoEncoder(make_opt(args.preset, b200_precision=args.precision, b200_max_batch=B,
+                                                 b200_cuda_graph=B if args.graph else 0), input_channel_scale=2)
     net.init_weights("kaiming")
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     net = net.to(dev).eval()
@@ -355,7 +355,8 @@ def run_ours(args):
                 dtype="bf16x3 operands, f32 accumulate" if nsplit == 3 else "bf16 operands, f32 accumulate",
                 data="synthetic",
                 config=dict(workload=workload_name(args), preset=args.preset, batch_per_gpu=B, global_batch=total,
-                            precision=args.precision, parallelism="dp%d (frames sharded, final pose gather)" % world,
+                            precision=args.precision, issue="cuda graph replay" if args.graph else "38 launches per step",
+                            parallelism="dp%d (frames sharded, final pose gather)" % world,
                             l2="inputs %.0f MB + activations >> 126 MB L2 per step, no flush needed" % (x.numel() * 4 / 1e6)),
                 e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, checked=e2e_ok),
@@ -544,7 +545,8 @@ def main():
                          "train = config 5 (optimisation step; reference batch size 32, scripts/train/PoseEstimator/*.sh)")
     ap.add_argument("--persistent-bptt", dest="persistent_bptt", action="store_true",
                     help="train workload: BPTT of each propagation layer as one persistent launch instead of per-joint launches")
-    ap.add_argument("--graph", action="store_true", help="train workload, 1 GPU: run forward+loss+backward from a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="train workload, 1 GPU: run forward+loss+backward from a CUDA graph; "
+                    "lifting workloads: replay the forward from a CUDA graph (opt b200_cuda_graph; small-batch serving)")
     ap.add_argument("--dump", default="", help="also write the JSON line + per-GEMM launch table to this file")
     args = ap.parse_args()
     if args.batch <= 0:

@@ -127,6 +127,8 @@ class EgoTAPAutoEncoder(nn.Module):
     Extra, optional ``opt`` fields (read with ``getattr`` so the reference's parser needs no change):
       ``b200_precision``  'bf16x3' (default; fp32-parity mode) or 'bf16' (throughput mode)
       ``b200_max_batch``  initial workspace batch (grows on demand)
+      ``b200_cuda_graph`` 0 (default) or N: batches of up to N frames replay the forward from a CUDA graph captured per batch
+                          size (small-batch serving: no per-launch host work, no tensor-map encoding on the call path)
     """
 
     def __init__(self, opt, input_channel_scale=1, fc_dim=16384):
@@ -165,6 +167,8 @@ class EgoTAPAutoEncoder(nn.Module):
         self._J = J
         self._precision = PRECISIONS[str(getattr(opt, "b200_precision", "bf16x3"))]
         self._max_batch = int(getattr(opt, "b200_max_batch", 0))
+        self._graph_max_batch = int(getattr(opt, "b200_cuda_graph", 0) or 0)
+        self._graphs = {}
         for key, shape, kind in _state_spec(J, self.use_global_offset):
             if kind == "count":
                 t = torch.tensor(0, dtype=torch.long)
@@ -214,6 +218,7 @@ class EgoTAPAutoEncoder(nn.Module):
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self._plan = None
+        self._graphs = {}
         self._packed_versions = None
         self._zeros = {}
         self._engine = None
@@ -226,6 +231,7 @@ class EgoTAPAutoEncoder(nn.Module):
             return
         lib = capi.lib()
         self._destroy_plan()
+        self._graphs = {}                  # captured graphs hold pointers into the plan's buffers
         preset = capi.PRESET_ID[self.joint_preset]
         pb, wb = C.c_size_t(), C.c_size_t()
         capi.check(lib.egotap_b200_plan_sizes(preset, self._precision, want, C.byref(pb), C.byref(wb)), "plan_sizes")
@@ -325,10 +331,35 @@ class EgoTAPAutoEncoder(nn.Module):
         with torch.cuda.device(x.device):
             self._ensure_plan(B, x.device)
             self._ensure_packed()
+            if last_stage == -1 and 0 < B <= self._graph_max_batch:
+                return self._run_graph(x, B)
             pose = torch.empty((B, self.num_joints, 3), dtype=torch.float32, device=x.device)
             capi.check(capi.lib().egotap_b200_forward(self._plan, C.c_void_p(x.data_ptr()), B, C.c_void_p(pose.data_ptr()),
                                                       last_stage, capi.current_stream()), "forward")
         return pose
+
+    def _run_graph(self, x, B):
+        """small-batch serving: the whole forward (38 launches) replayed from a CUDA graph captured once per batch size.  The
+        graph reads a module-owned input buffer and writes a module-owned pose buffer (stable pointers); the packed weights
+        are refreshed outside the graph (``_ensure_packed``), into the same buffers the graph reads."""
+        lib = capi.lib()
+        entry = self._graphs.get(B)
+        if entry is None:
+            static_in = torch.empty_like(x)
+            static_out = torch.empty((B, self.num_joints, 3), dtype=torch.float32, device=x.device)
+            static_in.copy_(x)
+            # one eager pass first: per-device function attributes are set on a kernel's first launch, not under capture
+            capi.check(lib.egotap_b200_forward(self._plan, C.c_void_p(static_in.data_ptr()), B, C.c_void_p(static_out.data_ptr()),
+                                               -1, capi.current_stream()), "forward")
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                capi.check(lib.egotap_b200_forward(self._plan, C.c_void_p(static_in.data_ptr()), B,
+                                                   C.c_void_p(static_out.data_ptr()), -1, capi.current_stream()), "forward (capture)")
+            entry = self._graphs[B] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
 
     def _zeros_like_reference(self, B, device):
         key = (B, device)
