@@ -299,7 +299,11 @@ def run_ours(args):
     # ---------------- roofline of the dominant kernel family (tcgen05 GEMM), per-launch CUDA events, one extra step
     pk = peaks()
     # rank 0 alone runs this extra step (the other ranks have left): it must not contain a collective
+    graph_batch, net._graph_max_batch = net._graph_max_batch, 0    # the per-kernel events need launched (not replayed) kernels
     all_recs = capi.profile_kernels(lambda: local_step())
+    net._graph_max_batch = graph_batch
+    if args.graph:
+        launches = K * len(all_recs)                                # kernels executed from the graph in the timed region
     recs = [r for r in all_recs if "flops" in r]
     gemm_ms = sum(r["ms"] for r in recs)
     gemm_flops = sum(r["flops"] for r in recs)
