@@ -36,6 +36,6 @@ for b in 1 8 32; do
   timeout 300 python bench.py --batch $b --steps 50 --warmup 5 --graph 2>&1 | tail -1 | cut -c1-260
   EGOTAP_SPLITK=1 timeout 300 python bench.py --batch $b --steps 50 --warmup 5 --graph 2>&1 | tail -1 | cut -c1-260
 done
-EGOTAP_ATTN=wide timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_wide -c 2 \
+EGOTAP_ATTN=wide timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_wide -c 1 \
     -o gpurun_out/r2b_attention_wide python tools/attn_only.py 64 bf16x3 > gpurun_out/r2b_ncu_attn.log 2>&1
 tail -3 gpurun_out/r2b_ncu_attn.log | cut -c1-300
