@@ -2,7 +2,7 @@
 section 11) reproduces -- the inference entry points against the oracle, the training step against autograd -- with every
 launch executed from the product's own .cu files.  No GPU involved; numbers are parity figures, not timings.
 
-    python tools/emu_report.py
+    python tests/studies/emu_report.py
 """
 import ctypes as C
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "cuda_emu")):
     sys.path.insert(0, p)
 

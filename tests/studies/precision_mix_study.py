@@ -1,7 +1,8 @@
 """CPU study: pose error of selective two-MMA tensor-core operand schemes vs the three-MMA bf16 hi/lo split.
 Uses the test oracle with emulated operand roundings; results in profiles/r01e_precision_mix_cpu.json."""
-import sys, contextlib
-sys.path[:0]=['/root/repo','/root/repo/oracle']
+import contextlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
 import torch, torch.nn.functional as F
 import egotap_oracle as orc, weights
 from egotap_b200.synthetic import synthetic_heatmaps

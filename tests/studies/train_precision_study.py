@@ -6,7 +6,7 @@
 -- for a number of AdamW steps on a fixed synthetic batch, recording the loss trajectory and the distance of the weights
 from the exact run.  Writes profiles/r01d_train_precision_cpu.json.
 
-    python tools/train_precision_study.py [--steps 12] [--batch 4]
+    python tests/studies/train_precision_study.py [--steps 12] [--batch 4]
 """
 import argparse
 import json
@@ -14,7 +14,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 
