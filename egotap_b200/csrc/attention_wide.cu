@@ -24,6 +24,18 @@
 
 namespace eb {
 
+// Debug-only wait-cycle accounting (tools/attn_trace.py builds a separate library with -DEB_ATTN_TRACE); no-ops otherwise.
+#ifdef EB_ATTN_TRACE
+__device__ unsigned long long g_attn_wide_trace[32];
+#define TW_DECL long long tw_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tw_t0_ = 0; (void)tw_t0_; const long long tw_start_ = clock64();
+#define TW_WAIT(i, stmt) { tw_t0_ = clock64(); stmt; tw_[i] += clock64() - tw_t0_; }
+#define TW_FLUSH(base, cond) { tw_[0] = clock64() - tw_start_; if (cond) { for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_attn_wide_trace[(base) + i_], (unsigned long long)tw_[i_]); } }
+#else
+#define TW_DECL
+#define TW_WAIT(i, stmt) { stmt; }
+#define TW_FLUSH(base, cond)
+#endif
+
 constexpr int AW_TOK = 576, AW_HEADS = 8, AW_D = 128, AW_QT = 128, AW_KT = 128;
 constexpr int AW_NT = (AW_TOK + AW_KT - 1) / AW_KT;          // 5 key tiles, the last one has 64 keys
 constexpr int AW_LAST_KEYS = AW_TOK - (AW_NT - 1) * AW_KT;   // 64
@@ -98,6 +110,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     // ------------------------------------------------------------------ TMA producer
     // ring order = MMA consumption order: K(0); then per global tile g: K(g+1), V(g).  Q is outside the ring.
     if (lane == 0) {
+      TW_DECL
       uint32_t rc = 0;
       auto item_coords = [&](int it, int& qt, int& h, int& b, int& bh) {
         const int item = int(blockIdx.x) + it * int(gridDim.x);
@@ -106,7 +119,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       auto load_q = [&](int it) {
         int qt, h, b, bh;
         item_coords(it, qt, h, b, bh);
-        mbar_wait(q_empty, (it & 1) ^ 1);
+        TW_WAIT(1, mbar_wait(q_empty, (it & 1) ^ 1));
         mbar_expect_tx(q_full, C::Q_BYTES);
         for (int kb = 0; kb < 2; ++kb) {
           tma_load_4d(sQ + kb * C::BLK, &tmQh, q_full, kb * 64, qt * AW_QT, h, b);
@@ -116,7 +129,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       auto slot_acquire = [&](uint64_t*& full) -> uint8_t* {
         const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
         ++rc;
-        mbar_wait(&kv_empty[slot], ph ^ 1);
+        TW_WAIT(2, mbar_wait(&kv_empty[slot], ph ^ 1));
         full = &kv_full[slot];
         mbar_expect_tx(full, C::GRAN_BYTES);
         return sRing + slot * C::GRAN_BYTES;
@@ -152,6 +165,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         }
         load_v(g);
       }
+      TW_FLUSH(16, true)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (all lanes run the loop; the
@@ -161,18 +175,19 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     constexpr uint32_t idesc_o = make_idesc_bf16(AW_QT, AW_D);
     const uint32_t q_lo = sdesc_lo(smem_u32(sQ)), ring_lo = sdesc_lo(smem_u32(sRing));
     uint32_t rc = 0;
+    TW_DECL
     auto slot_wait = [&](uint32_t& slot) -> uint32_t {
       slot = rc % C::NSLOTS;
       const uint32_t ph = (rc / C::NSLOTS) & 1;
       ++rc;
-      mbar_wait(&kv_full[slot], ph);
+      TW_WAIT(2, mbar_wait(&kv_full[slot], ph));
       return ring_lo + ((slot * C::GRAN_BYTES) >> 4);
     };
     auto issue_s = [&](int g) {
       const int it = g / AW_NT, j = g % AW_NT;
       const uint32_t d = C::T_S + uint32_t(g & 1) * 128u;
       const uint32_t idesc = j == AW_NT - 1 ? idesc_s_last : idesc_s;
-      if (j == 0) mbar_wait(q_full, it & 1);
+      if (j == 0) TW_WAIT(1, mbar_wait(q_full, it & 1));
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         uint32_t slot;
@@ -199,8 +214,8 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       const int it = g / AW_NT, j = g % AW_NT;
       const uint32_t t_o = C::T_O + uint32_t(it & 1) * AW_D;
       const uint32_t t_p = C::T_S + uint32_t(g & 1) * 128u;
-      if (j == 0) mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1);   // the epilogue drained this O buffer (two items ago)
-      mbar_wait(&p_full[g & 1], (g >> 1) & 1);
+      if (j == 0) TW_WAIT(5, mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1));   // the epilogue drained this O buffer (two items ago)
+      TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
       const int ngran = j == AW_NT - 1 ? AW_LAST_KEYS / 64 : AW_KT / 64;
       for (int kg = 0; kg < ngran; ++kg) {
         uint32_t slot;
@@ -227,6 +242,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       if (g + 1 < my_tiles) issue_s(g + 1);
       issue_pv(g);
     }
+    TW_FLUSH(0, lane == 0)
   } else if (warp < 10) {
     // ------------------------------------------------------------------ softmax warps (8)
     // Warps w and w+4 own the same TMEM lane quarter (query rows) and split the keys of a tile into two halves; the
@@ -238,6 +254,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     const float c = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
     float m_ref = 0.f, l = 0.f;
+    TW_DECL
 #pragma unroll 1
     for (int g = 0; g < my_tiles; ++g) {
       const int it = g / AW_NT, j = g % AW_NT;
@@ -247,7 +264,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       const bool full_tile = j != AW_NT - 1;      // this warp: 64 keys of a full tile, 32 of the last one
       const uint32_t col0 = full_tile ? hf * 64 : hf * 32;
       if (j == 0) l = 0.f;
-      mbar_wait(&s_full[sb], par);
+      TW_WAIT(1, mbar_wait(&s_full[sb], par));
       tc_fence_after();
       uint32_t r0[32], r1[32];
       tmem_ld32(t_s + col0, r0);
@@ -263,7 +280,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       float* xm = xmax + (g & 1) * 256;
       xm[hf * 128 + row] = mt;
       tc_fence_before();
-      named_bar_sync<64>(1 + q);
+      TW_WAIT(2, named_bar_sync<64>(1 + q));
       tc_fence_after();
       mt = fmaxf(mt, xm[(hf ^ 1) * 128 + row]);
       if (j == 0) m_ref = mt;
@@ -272,7 +289,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       if (need) { f = ex2_approx((m_ref - mt) * c); m_ref = mt; l *= f; }
       const float mc = m_ref * c;
       if (__any_sync(0xffffffffu, need)) {        // lazy rescale of this warp's 64 O columns: needs PV_{g-1} complete
-        mbar_wait(&pv_done[sb ^ 1], uint32_t((g - 1) >> 1) & 1u);
+        TW_WAIT(3, mbar_wait(&pv_done[sb ^ 1], uint32_t((g - 1) >> 1) & 1u));
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < 2; ++ch) {
@@ -316,17 +333,19 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
+    TW_FLUSH(8, warp == 2 && lane == 0)
   } else {
     // ------------------------------------------------------------------ epilogue warps (4): O / l -> ctx rows
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     int it = 0;
+    TW_DECL
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int qt = item % qtiles, bh = item / qtiles;
       const int h = bh % AW_HEADS, b = bh / AW_HEADS;
       const int ob = it & 1;
-      mbar_wait(&o_full[ob], (it >> 1) & 1);
+      TW_WAIT(1, mbar_wait(&o_full[ob], (it >> 1) & 1));
       tc_fence_after();
       const float inv = 1.0f / (lsum[ob * 256 + row] + lsum[ob * 256 + 128 + row]);
       const int tok = qt * AW_QT + row;
@@ -358,6 +377,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
     }
+    TW_FLUSH(24, warp == 10 && lane == 0)
   }
 
   tc_fence_before();
@@ -410,3 +430,11 @@ int attention_wide_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, c
 }
 
 }  // namespace eb
+
+#ifdef EB_ATTN_TRACE
+extern "C" int egotap_b200_attn_wide_trace(unsigned long long* out32, int reset) {
+  if (out32) cudaMemcpyFromSymbol(out32, eb::g_attn_wide_trace, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(eb::g_attn_wide_trace, z, sizeof(z)); }
+  return 0;
+}
+#endif

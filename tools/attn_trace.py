@@ -1,11 +1,13 @@
-"""Debug: wait-cycle accounting of the attention kernel's warp roles (library built with -DEB_ATTN_TRACE)."""
+"""Debug: wait-cycle accounting of the attention kernels' warp roles (library built with -DEB_ATTN_TRACE).
+EGOTAP_ATTN=wide traces attention_wide_kernel instead of attention_kernel."""
 import ctypes as C, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 lib = os.path.join(ROOT, "tools", "libtrace.so")
 if not os.path.isfile(lib) or "--build" in sys.argv:
     os.makedirs(os.path.dirname(lib), exist_ok=True)
-    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "metrics.cu", "plan.cu")]
+    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "attention_wide.cu", "pu_chain.cu", "pu_chain_bwd.cu",
+                                                                       "metrics.cu", "plan.cu", "train_ops.cu", "train_model.cu", "gt_heatmap.cu")]
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
                            "-DEB_ATTN_TRACE", "-o", lib] + src)
 if "--build" in sys.argv:
@@ -14,6 +16,8 @@ import torch
 from egotap_b200 import capi
 capi.LIB_PATH = lib
 L = capi.lib()
+wide = os.environ.get("EGOTAP_ATTN") == "wide"
+trace = L.egotap_b200_attn_wide_trace if wide else L.egotap_b200_attn_trace
 Bf = 256
 for prec, name in ((capi.PREC_BF16X3, "x3"), (capi.PREC_BF16, "bf16")):
     x3 = prec == capi.PREC_BF16X3
@@ -21,12 +25,18 @@ for prec, name in ((capi.PREC_BF16X3, "x3"), (capi.PREC_BF16, "bf16")):
     qh, ql = capi.split_bf16(qk); vh, vl = capi.split_bf16(vt)
     capi.attention(qh, ql if x3 else None, vh, vl if x3 else None, Bf, prec); torch.cuda.synchronize()
     out = (C.c_ulonglong * 32)()
-    L.egotap_b200_attn_trace(out, 1)
+    trace(out, 1)
     capi.attention(qh, ql if x3 else None, vh, vl if x3 else None, Bf, prec); torch.cuda.synchronize()
-    L.egotap_b200_attn_trace(out, 1)
+    trace(out, 1)
     v = [x / 148.0 for x in out]
     items = Bf * 8 * 5 / 148.0
-    print("== %s  (cycles per CTA, %.1f items per CTA)" % (name, items))
+    print("== %s %s (cycles per CTA, %.1f items per CTA)" % ("attention_wide_kernel" if wide else "attention_kernel", name, items))
+    if wide:
+        print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  p_full %.0f  o_empty %.0f | per item %.0f" % (v[0], v[1], v[2], v[4], v[5], v[0] / items))
+        print(" softmax  : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(rescale) %.0f" % (v[8], v[9], v[10], v[11]))
+        print(" producer : total %.0f | wait q_empty %.0f  kv_empty %.0f" % (v[16], v[17], v[18]))
+        print(" epilogue : total %.0f | wait o_full %.0f" % (v[24], v[25]))
+        continue
     print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  s_empty %.0f  p_full %.0f | per item %.0f" % (v[0], v[1], v[2], v[3], v[4], v[0] / items))
     print(" softmax  : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(P buf) %.0f  pv_done(last) %.0f  epilogue %.0f" % (v[8], v[9], v[10], v[11], v[12], v[13]))
     print(" producer : total %.0f | wait q_empty %.0f  kv_empty %.0f" % (v[16], v[17], v[18]))

@@ -22,6 +22,9 @@ for prec in bf16x3 bf16; do
   done
 done
 unset EGOTAP_ATTN
+# wait-cycle accounting of both attention kernels (a -DEB_ATTN_TRACE build of the library, tools/libtrace.so)
+timeout 200 python tools/attn_trace.py 2>&1 | tail -12
+EGOTAP_ATTN=wide timeout 200 python tools/attn_trace.py 2>&1 | tail -12
 for prec in bf16x3 bf16; do
   timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_v1.json 2>&1 | tail -1 | cut -c1-700
   EGOTAP_ATTN=wide timeout 600 python bench.py --precision $prec --steps 20 --warmup 3 --dump gpurun_out/r2b_bench_${prec}_wide.json 2>&1 | tail -1 | cut -c1-700
