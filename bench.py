@@ -307,6 +307,8 @@ def run_ours(args):
     recs = [r for r in all_recs if "flops" in r]
     gemm_ms = sum(r["ms"] for r in recs)
     gemm_flops = sum(r["flops"] for r in recs)
+    if not recs or gemm_ms <= 0:
+        raise SystemExit("bench: the per-kernel profile of one step recorded no GEMM launch -- the CUDA path did not run")
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     nsplit = 3 if args.precision != "bf16" else 1
     # DRAM traffic of the same launches from the committed ncu capture (profiles/), when it is for this configuration
