@@ -520,6 +520,7 @@ print("RESULT " + json.dumps(dict(launches=lib.emu_set_dry_run(0), workspace_gb=
     ("infer", "UnrealEgo", 256, "bf16x3", ""),                # BASELINE config 2 (the bench default)
     ("infer", "EgoCap", 1024, "bf16", ""),                    # config 3 on one GPU
     ("infer", "UnrealEgo", 32, "bf16x3", "EGOTAP_SPLITK=1"),
+    ("infer", "UnrealEgo", 1024, "bf16x3", "EGOTAP_ATTN=wide EGOTAP_EPI=coalesced"),   # both opt-in kernels at the largest size
 ])
 def test_full_size_steps_pass_the_host_checks_and_launch_limits(kind, preset, batch, prec, extra):
     """Dry run at BASELINE.json's real batch sizes: the whole training step / inference forward is driven through the library
@@ -532,8 +533,9 @@ def test_full_size_steps_pass_the_host_checks_and_launch_limits(kind, preset, ba
     here = os.path.dirname(os.path.abspath(__file__))
     code = _DRY_CODE % ([os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), os.path.join(here, "cuda_emu")],)
     e = dict(os.environ)
-    if "=" in extra:
-        e[extra.split("=")[0]] = extra.split("=")[1]
+    for kv in extra.split():
+        if "=" in kv:
+            e[kv.split("=")[0]] = kv.split("=")[1]
     r = subprocess.run([sys.executable, "-c", code, kind, preset, str(batch), prec, extra or "-"], capture_output=True, text=True,
                        env=e, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
