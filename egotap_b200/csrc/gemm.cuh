@@ -165,8 +165,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row,
 // access of the warp then covers 4 full 128-byte lines (fp32) or 4 x 64 contiguous bytes (bf16 hi / lo).  The pointwise
 // part runs in the row domain, the residual add and the stores in the transposed domain; results are identical.
 struct EpiRowsT {            // transposed-domain addressing of the 8 rows a lane touches, fixed per tile
-  int orow[8], rrow[8];      // output / residual row of tile row 4 i + lane / 8 (row counts stay far below 2^31)
-  int cs[8];                 // column shift of that row (STORE_JOINT_REGROUP / STORE_HEAD_MERGE)
+  int orow[8];               // output row of tile row 4 i + lane / 8 (row counts stay far below 2^31)
   unsigned ok;               // bit i: the row exists
 };
 __device__ __forceinline__ EpiRowsT epi_rows_t(const EpiRow& row, bool row_ok, int lane) {
@@ -177,20 +176,31 @@ __device__ __forceinline__ EpiRowsT epi_rows_t(const EpiRow& row, bool row_ok, i
   for (int i = 0; i < 8; ++i) {
     const int rr = 4 * i + sub;
     t.orow[i] = __shfl_sync(0xffffffffu, int(row.orow), rr);
-    t.rrow[i] = __shfl_sync(0xffffffffu, int(row.rrow), rr);
-    t.cs[i] = __shfl_sync(0xffffffffu, row.col_shift, rr);
     t.ok |= unsigned(__shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr)) << i;
   }
   return t;
 }
-__device__ __forceinline__ void epi_load_resid_t(const EpiParams& p, const EpiRowsT& rows, int n0, int lane, float4 (&t)[8]) {
-  const int c0 = n0 + p.col_off + (lane & 7) * 4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if ((rows.ok >> i) & 1u) t[i] = *reinterpret_cast<const float4*>(p.resid + (long long)rows.rrow[i] * p.resid_ld + c0 + rows.cs[i]);
+// Residual row and column shift of tile row rr: equal to the output row / zero in the common layouts, fetched from the row's
+// owner (warp shuffle, all lanes participate: the conditions are warp-uniform) only in the modes where they differ.
+__device__ __forceinline__ void epi_row_extras(const EpiParams& p, const EpiRow& row, int orow_i, int rr, int& rrow, int& cs) {
+  rrow = orow_i;
+  cs = 0;
+  if (p.resid_mod > 0) rrow = __shfl_sync(0xffffffffu, int(row.rrow), rr);
+  if (p.store == STORE_JOINT_REGROUP || p.store == STORE_HEAD_MERGE) cs = __shfl_sync(0xffffffffu, row.col_shift, rr);
 }
-__device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const EpiRowsT& rows, int n0, uint32_t (&r)[32],
-                                                    const float4 (&t)[8], float4* stg, int lane) {
+__device__ __forceinline__ void epi_load_resid_t(const EpiParams& p, const EpiRow& row, const EpiRowsT& rows, int n0, int lane,
+                                                 float4 (&t)[8]) {
+  const int c0 = n0 + p.col_off + (lane & 7) * 4;
+  const int sub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int rrow, cs;
+    epi_row_extras(p, row, rows.orow[i], 4 * i + sub, rrow, cs);
+    if ((rows.ok >> i) & 1u) t[i] = *reinterpret_cast<const float4*>(p.resid + (long long)rrow * p.resid_ld + c0 + cs);
+  }
+}
+__device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const EpiRow& row, const EpiRowsT& rows, int n0,
+                                                    uint32_t (&r)[32], const float4 (&t)[8], float4* stg, int lane) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -225,9 +235,11 @@ __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const Ep
   for (int i = 0; i < 8; ++i) {
     const int rr = 4 * i + sub;
     float4 x = stg[rr * 8 + (seg ^ (rr & 7))];
+    int rrow_unused, cs;
+    epi_row_extras(p, row, rows.orow[i], rr, rrow_unused, cs);
     if ((rows.ok >> i) & 1u) {
       if (p.resid) { x.x += t[i].x; x.y += t[i].y; x.z += t[i].z; x.w += t[i].w; }
-      const long long o = (long long)rows.orow[i] * p.ldo + n0 + p.col_off + rows.cs[i] + seg * 4;
+      const long long o = (long long)rows.orow[i] * p.ldo + n0 + p.col_off + cs + seg * 4;
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
       if (p.out_hi) {
         uint32_t h0, l0, h1, l1;
@@ -405,12 +417,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           uint32_t r[32];
           tmem_ld32(t_addr + col_base + c * 32, r);
           // coalesced residual loads of this chunk, in flight across the TMEM wait, the pointwise math and the staging
-          if (ep.resid != nullptr && !v_part) epi_load_resid_t(ep, rows, n0, lane, t_cur);
+          if (ep.resid != nullptr && !v_part) epi_load_resid_t(ep, row, rows, n0, lane, t_cur);
           tmem_ld_wait();
           if (v_part) {
             if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur);
           } else {
-            epi_apply_coalesced(ep, rows, n0, r, t_cur, stg, lane);
+            epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane);
           }
         }
         tc_fence_before();
