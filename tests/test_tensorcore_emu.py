@@ -358,7 +358,9 @@ def test_persistent_chain_kernel(frames, J, x3):
 
 _INFER_CASES = [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
                 ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
-                ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"})]
+                ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"}),
+                # both opt-in kernels in the one-MMA bf16 mode (EMU_PREC is read by the child below, not by the library)
+                ("EgoCap", {"EGOTAP_ATTN": "wide", "EGOTAP_EPI": "coalesced", "EMU_PREC": "1"})]
 _INFER_CODE = r'''
 import ctypes as C, json, os, sys
 sys.path[:0] = %r
@@ -368,14 +370,15 @@ preset = %r
 lib = C.CDLL(build_emu.build()); lib.egotap_b200_last_error.restype = C.c_char_p; lib.egotap_b200_param_name.restype = C.c_char_p
 lib.emu_set_num_sms(32)
 pid = 0 if preset == "UnrealEgo" else 1
+prec = int(os.environ.get("EMU_PREC", "0"))
 pb, wb = C.c_size_t(), C.c_size_t()
 lib.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-assert lib.egotap_b200_plan_sizes(pid, 0, 1, C.byref(pb), C.byref(wb)) == 0
+assert lib.egotap_b200_plan_sizes(pid, prec, 1, C.byref(pb), C.byref(wb)) == 0
 packed = torch.zeros(pb.value + 1024, dtype=torch.uint8); work = torch.full((wb.value // 4 + 256,), float("nan"))
 al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
 plan = C.c_void_p()
 lib.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-assert lib.egotap_b200_plan_create(pid, 0, 1, al(packed), al(work), C.byref(plan)) == 0
+assert lib.egotap_b200_plan_create(pid, prec, 1, al(packed), al(work), C.byref(plan)) == 0
 sd = weights.make_state_dict(preset, seed=5)
 names = [lib.egotap_b200_param_name(pid, i).decode() for i in range(lib.egotap_b200_num_params(pid))]
 tens = [sd[n].float().contiguous() for n in names]
@@ -466,7 +469,10 @@ def test_whole_inference_path_on_product_source(preset, env, state_dicts):
     rc, text = _collect(key, timeout=1500)
     assert rc == 0, text[-1500:]
     rep = json.loads([l for l in text.splitlines() if l.startswith("RESULT ")][0][7:])
-    assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep       # the GPU parity tests' own bounds
+    if env.get("EMU_PREC") == "1":
+        assert rep["rel"] <= 5e-2 and rep["mpjpe_delta_mm"] <= 0.5, rep    # the bf16-operand mode's own stated bound
+    else:
+        assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep   # the GPU parity tests' own bounds
 
 
 _DRY_CODE = r'''
