@@ -14,7 +14,7 @@
 //   * one software pipeline over the GLOBAL tile sequence of a persistent CTA (5 tiles per work item, buffers alternate
 //     across item boundaries):  S_0; for g: { S_{g+1}; PV_g }  -- the score MMAs of the next item's first tile run
 //     while the softmax warps finish the current item.
-// Shared memory: Q tile (hi/lo) + a ring of 32 KB granules (one 64-wide d block of a 128-key K tile, or one 64-key
+// Shared memory: Q tile (hi/lo; two of them in bf16 mode) + a ring of 32 KB granules (one 64-wide d block of a 128-key K tile, or one 64-key
 // block of a V^T tile), consumed in MMA order.
 //   warp 0   TMA producer      warp 1   MMA issuer      warps 2-9  softmax (pairs split the keys of a tile)
 //   warps 10-13  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
@@ -49,14 +49,17 @@ struct AttnWideCfg {
   static constexpr int Q_BYTES = NOPS * 2 * BLK;             // [hi d0-63][hi d64-127][lo d0-63][lo d64-127]
   static constexpr int GRAN_BYTES = NOPS * BLK;              // K granule: [hi][lo] of one d block; V^T granule: [hi][lo] of one key block
   static constexpr int NSLOTS = NSPLIT == 1 ? 8 : 4;
-  static constexpr int BAR_OFF = Q_BYTES + NSLOTS * GRAN_BYTES;
+  // bf16 mode has room for two Q tiles: the next item's Q is loaded a whole item ahead.  In the parity mode the single Q
+  // buffer is reloaded when the item's last score tile has been computed; the tile is prefetched into L2 an item ahead.
+  static constexpr int QBUF = NSPLIT == 1 ? 2 : 1;
+  static constexpr int BAR_OFF = QBUF * Q_BYTES + NSLOTS * GRAN_BYTES;
   static constexpr int XCHG_OFF = BAR_OFF + 256;             // [2][2][128] row maxima, then [2][2][128] row sums
   static constexpr int SMEM_BYTES = XCHG_OFF + 4096;         // base must be 1 KB aligned (checked)
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
   static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(2 + 2 * NSLOTS + 10 + 1 <= 32, "barrier block");
+  static_assert(2 * QBUF + 2 * NSLOTS + 10 + 1 <= 32, "barrier block");
 };
 
 template <int NSPLIT>
@@ -68,11 +71,11 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
   EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint8_t* sQ = smem;
-  uint8_t* sRing = smem + C::Q_BYTES;
+  uint8_t* sRing = smem + C::QBUF * C::Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
-  uint64_t* q_full = bars;                  // [1]
-  uint64_t* q_empty = bars + 1;             // [1]  last score tile of an item has been computed
-  uint64_t* kv_full = bars + 2;             // [NSLOTS]
+  uint64_t* q_full = bars;                  // [QBUF]
+  uint64_t* q_empty = bars + C::QBUF;       // [QBUF]  last score tile of an item has been computed
+  uint64_t* kv_full = bars + 2 * C::QBUF;   // [NSLOTS]
   uint64_t* kv_empty = kv_full + C::NSLOTS;
   uint64_t* s_full = kv_empty + C::NSLOTS;  // [2]  S_g in TMEM
   uint64_t* p_full = s_full + 2;            // [2]  P_g in TMEM (over S_g)
@@ -92,7 +95,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     if (NSPLIT > 1) { tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmVl); }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < C::QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
@@ -119,11 +122,21 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       auto load_q = [&](int it) {
         int qt, h, b, bh;
         item_coords(it, qt, h, b, bh);
-        TW_WAIT(1, mbar_wait(q_empty, (it & 1) ^ 1));
-        mbar_expect_tx(q_full, C::Q_BYTES);
+        const int qb = it % C::QBUF;
+        uint8_t* dst = sQ + qb * C::Q_BYTES;
+        TW_WAIT(1, mbar_wait(&q_empty[qb], ((it / C::QBUF) & 1) ^ 1));
+        mbar_expect_tx(&q_full[qb], C::Q_BYTES);
         for (int kb = 0; kb < 2; ++kb) {
-          tma_load_4d(sQ + kb * C::BLK, &tmQh, q_full, kb * 64, qt * AW_QT, h, b);
-          if (NSPLIT > 1) tma_load_4d(sQ + (2 + kb) * C::BLK, &tmQl, q_full, kb * 64, qt * AW_QT, h, b);
+          tma_load_4d(dst + kb * C::BLK, &tmQh, &q_full[qb], kb * 64, qt * AW_QT, h, b);
+          if (NSPLIT > 1) tma_load_4d(dst + (2 + kb) * C::BLK, &tmQl, &q_full[qb], kb * 64, qt * AW_QT, h, b);
+        }
+      };
+      auto prefetch_q = [&](int it) {      // L2 prefetch of a Q tile that will be loaded when its buffer is free
+        int qt, h, b, bh;
+        item_coords(it, qt, h, b, bh);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_prefetch_4d(&tmQh, kb * 64, qt * AW_QT, h, b);
+          if (NSPLIT > 1) tma_prefetch_4d(&tmQl, kb * 64, qt * AW_QT, h, b);
         }
       };
       auto slot_acquire = [&](uint64_t*& full) -> uint8_t* {
@@ -159,8 +172,12 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       };
       if (my_tiles > 0) { load_q(0); load_k(0); }
       for (int g = 0; g < my_tiles; ++g) {
+        const int it = g / AW_NT;
+        if (g % AW_NT == 0 && it + 1 < my_items) {
+          if (C::QBUF == 2) load_q(it + 1); else prefetch_q(it + 1);
+        }
         if (g + 1 < my_tiles) {
-          if ((g + 1) % AW_NT == 0) load_q((g + 1) / AW_NT);
+          if (C::QBUF == 1 && (g + 1) % AW_NT == 0) load_q((g + 1) / AW_NT);
           load_k(g + 1);
         }
         load_v(g);
@@ -173,7 +190,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
     constexpr uint32_t idesc_s = make_idesc_bf16(AW_QT, AW_KT);
     constexpr uint32_t idesc_s_last = make_idesc_bf16(AW_QT, AW_LAST_KEYS);
     constexpr uint32_t idesc_o = make_idesc_bf16(AW_QT, AW_D);
-    const uint32_t q_lo = sdesc_lo(smem_u32(sQ)), ring_lo = sdesc_lo(smem_u32(sRing));
+    const uint32_t q_lo0 = sdesc_lo(smem_u32(sQ)), ring_lo = sdesc_lo(smem_u32(sRing));
     uint32_t rc = 0;
     TW_DECL
     auto slot_wait = [&](uint32_t& slot) -> uint32_t {
@@ -187,7 +204,9 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
       const int it = g / AW_NT, j = g % AW_NT;
       const uint32_t d = C::T_S + uint32_t(g & 1) * 128u;
       const uint32_t idesc = j == AW_NT - 1 ? idesc_s_last : idesc_s;
-      if (j == 0) TW_WAIT(1, mbar_wait(q_full, it & 1));
+      const int qb = it % C::QBUF;
+      const uint32_t q_lo = q_lo0 + ((qb * C::Q_BYTES) >> 4);
+      if (j == 0) TW_WAIT(1, mbar_wait(&q_full[qb], (it / C::QBUF) & 1));
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         uint32_t slot;
@@ -208,7 +227,7 @@ attention_wide_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_con
         umma_commit<1>(&kv_empty[slot]);
       }
       umma_commit<1>(&s_full[g & 1]);
-      if (j == AW_NT - 1) umma_commit<1>(q_empty);
+      if (j == AW_NT - 1) umma_commit<1>(&q_empty[qb]);
     };
     auto issue_pv = [&](int g) {
       const int it = g / AW_NT, j = g % AW_NT;

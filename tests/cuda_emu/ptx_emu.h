@@ -106,6 +106,7 @@ inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0,
   for (uint32_t i = 0; i < tm.box_rows * 64; ++i) { const uint16_t nan = 0x7fc0; memcpy(dst + i * 2, &nan, 2); }
   eb_emu::defer([=]() { tma_load_now(dst, &tm, bar, c0, c1, c2, c3); });
 }
+inline void tma_prefetch_4d(const CUtensorMap*, int, int, int, int) {}   // L2 prefetch: no functional effect
 inline void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   tma_load_to(reinterpret_cast<uint8_t*>(dst), tm, bar, c0, c1, c2, c3);
 }
