@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 inference A/B job: first hardware run of the opt-in variants written after round 1's GPU budget was spent.
-#   gpurun --timeout 1200 -- 'bash tools/gpu_job_r2b.sh > gpurun_out/r2b.log 2>&1'
+#   gpurun --timeout 2700 -- 'bash tools/gpu_job_r2b.sh > gpurun_out/r2b.log 2>&1'
 # 1. parity of the wide attention kernel (EGOTAP_ATTN=wide) op-level and through the whole path (subprocess per case)
 # 2. the attention op alone, v1 vs wide, both precisions (CUDA events)           -> is 128-key tiling faster?
 # 3. bench lines of the default workload with / without it, both precisions       -> step-level effect
