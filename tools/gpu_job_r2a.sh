@@ -1,6 +1,6 @@
 #!/bin/bash
 # First hardware run of the training step + GT-heatmap kernel (written in round 1 after the GPU budget was spent):
-#   gpurun --timeout 1500 -- 'bash tools/gpu_job_r2a.sh > gpurun_out/r2a.log 2>&1'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_job_r2a.sh > gpurun_out/r2a.log 2>&1'
 # 1. op-level parity of every training kernel and of gt_heatmap_kernel against their oracles
 # 2. engine-level parity (gradients vs autograd oracle, determinism, module loop, CUDA-graph step)
 # 3. first bench lines of config 5 (bf16 and parity mode, batch 32 = the reference's, and 256) with per-kernel tables
