@@ -362,6 +362,7 @@ def run_ours(args):
                 data="synthetic",
                 config=dict(workload=workload_name(args), preset=args.preset, batch_per_gpu=B, global_batch=total,
                             precision=args.precision, issue="cuda graph replay" if args.graph else "38 launches per step",
+                            switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("EGOTAP_")},   # A/B switches in effect
                             parallelism="dp%d (frames sharded, final pose gather)" % world,
                             l2="inputs %.0f MB + activations >> 126 MB L2 per step, no flush needed" % (x.numel() * 4 / 1e6)),
                 e2e=dict(value=total * K / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
