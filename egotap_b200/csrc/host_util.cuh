@@ -64,9 +64,12 @@ inline std::atomic<long long>& launch_counter() {
 #define EB_LAUNCH_CLUSTER(kernel, grid, block, smem, cluster, stream, ...) \
   eb::launch_cluster(kernel, grid, block, smem, cluster, stream, __VA_ARGS__)
 #define EB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-// kernels whose CTAs synchronise through global memory: every CTA of the grid must be co-resident (the caller sizes the
-// grid accordingly); the emulation runs the whole grid concurrently
-#define EB_LAUNCH_GRID_SYNC(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+// kernels whose CTAs synchronise through global memory: every CTA of the grid must be co-resident.  A cooperative launch is
+// all-or-nothing for residency (the driver rejects a grid that cannot be co-resident and never schedules part of it next to
+// another stream's kernel), so two such kernels on different streams cannot dead-lock each other; the emulation runs the whole
+// grid concurrently
+#define EB_LAUNCH_GRID_SYNC(kernel, grid, block, smem, stream, ...) \
+  eb::launch_cooperative(kernel, grid, block, smem, stream, __VA_ARGS__)
 #endif
 
 #ifdef EB_HOST_EMU
@@ -201,6 +204,22 @@ inline cudaError_t launch_cluster(Kernel kernel, unsigned grid, unsigned block, 
   attr[0].val.clusterDim.x = unsigned(cluster);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+template <class Kernel, class... Args>
+inline cudaError_t launch_cooperative(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);

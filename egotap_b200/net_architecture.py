@@ -99,12 +99,17 @@ class _LiftTrainFn(torch.autograd.Function):
         pose = eng.forward(x)
         out = eng.be.empty(tuple(pose.shape), torch.float32)
         eng.be.copy(out, pose)          # the engine's pose buffer is reused by the next step
-        ctx.module, ctx.names = module, names
+        ctx.module, ctx.names, ctx.fwd_gen = module, names, eng.fwd_gen
         return out
 
     @staticmethod
     def backward(ctx, dpose):
         eng = ctx.module._engine
+        if eng is None or eng.fwd_gen != ctx.fwd_gen:
+            # the engine keeps ONE set of saved activations: a second train-mode forward before this backward has replaced them
+            raise RuntimeError("egotap_b200: backward of a train-mode forward whose activations were overwritten by a later "
+                               "forward of the same module (one forward -> one backward; for gradient accumulation call "
+                               "backward() after each forward)")
         d = dpose.contiguous()
         if d.dtype != torch.float32:
             d = d.float()
@@ -185,7 +190,7 @@ class EgoTAPAutoEncoder(nn.Module):
         self._packed_versions = None
         self._zeros = {}
         self._engine = None
-        self._engine_backend = None      # tests inject the op oracle here; the product default is the CUDA library
+        self._engine_mutation_seen = 0
         self.skel_inputs = None
         self.skel_embed = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
@@ -222,13 +227,18 @@ class EgoTAPAutoEncoder(nn.Module):
         self._packed_versions = None
         self._zeros = {}
         self._engine = None
+        self._engine_mutation_seen = 0
         return r
 
     def _ensure_plan(self, batch, device):
-        want = max(batch, self._max_batch, 1)
         key = (device, self._precision)
         if self._plan is not None and self._plan_key == key and self._plan_batch >= batch:
             return
+        # sized for the largest batch known up front (b200_max_batch, the CUDA-graph limit) and grown geometrically after
+        # that: every growth re-creates the workspace, which drops the captured graphs (they are re-captured lazily)
+        want = max(batch, self._max_batch, self._graph_max_batch, 1)
+        if self._plan is not None and self._plan_key == key:
+            want = max(want, 2 * self._plan_batch)
         lib = capi.lib()
         self._destroy_plan()
         self._graphs = {}                  # captured graphs hold pointers into the plan's buffers
@@ -263,9 +273,10 @@ class EgoTAPAutoEncoder(nn.Module):
         return [sd[lib.egotap_b200_param_name(preset, i).decode()] for i in range(n)]
 
     def _ensure_packed(self):
-        # the engine's own AdamW writes the parameters through raw pointers: tensor version counters do not see it
-        if self._engine is not None and self._engine.opt_step != getattr(self, "_engine_step_seen", 0):
-            self._engine_step_seen = self._engine.opt_step
+        # the engine writes parameters (AdamW) and BatchNorm running buffers (train-mode forward) through raw pointers:
+        # tensor version counters do not see it, the engine's own mutation counter does
+        if self._engine is not None and self._engine.mutation != self._engine_mutation_seen:
+            self._engine_mutation_seen = self._engine.mutation
             self._packed_versions = None
         tensors = self._param_list()
         versions = tuple((t.data_ptr(), t._version) for t in tensors)
@@ -287,14 +298,22 @@ class EgoTAPAutoEncoder(nn.Module):
             tensors = {k: v.data for k, v in self.named_parameters()}
             tensors.update({k: v for k, v in self.named_buffers()})
             precision = "bf16" if self._precision == capi.PREC_BF16 else "bf16x3"
-            self._engine = TrainEngine(self.joint_preset, tensors, precision=precision, backend=self._engine_backend)
+            self._engine = self._make_engine(TrainEngine, tensors, precision)
+            self._engine_mutation_seen = 0
         return self._engine
+
+    def _make_engine(self, engine_cls, tensors, precision):
+        return engine_cls(self.joint_preset, tensors, precision=precision)     # backend: the CUDA library, or it raises
+
+    @staticmethod
+    def _check_device(input):
+        if not isinstance(input, torch.Tensor) or not input.is_cuda:
+            raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
 
     def _run_train(self, input):
         """train-mode forward (BatchNorm1d batch statistics, running buffers updated) with an autograd graph to
         every trained parameter (reference: the same nn.Module under .train(), model/network_utils.py:123-142)"""
-        if self._engine_backend is None and not input.is_cuda:
-            raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
+        self._check_device(input)
         assert input.dim() == 4 and input.size(1) == self.channels_heatmap and input.size(2) == self.W and input.size(3) == self.H, \
             "expected (B, %d, %d, %d) heatmaps, got %s" % (self.channels_heatmap, self.W, self.H, tuple(input.shape))
         x = input.detach()
@@ -315,8 +334,7 @@ class EgoTAPAutoEncoder(nn.Module):
     def _run(self, input, last_stage=-1):
         if self.training and isinstance(input, torch.Tensor) and input.size(0) > 0:
             return self._run_train(input)
-        if not isinstance(input, torch.Tensor) or not input.is_cuda:
-            raise RuntimeError("egotap_b200 has no CPU path: input must be a CUDA tensor")
+        EgoTAPAutoEncoder._check_device(input)
         if next(self.parameters()).device != input.device:
             raise RuntimeError("egotap_b200: parameters are on %s but input is on %s" % (next(self.parameters()).device, input.device))
         assert input.dim() == 4 and input.size(1) == self.channels_heatmap and input.size(2) == self.W and input.size(3) == self.H, \

@@ -145,6 +145,8 @@ class TrainEngine:
         self.grad = {k: self.flat_grad[o:o + params[k].numel()].view(params[k].shape) for k, o in self.offsets.items()}
         self.opt_m = self.opt_v = None
         self.opt_step = 0
+        self.mutation = 0          # bumped whenever the engine writes parameters or BatchNorm buffers through raw pointers
+        self.fwd_gen = 0           # bumped by every forward: a backward belongs to exactly one forward's activations
         self.batch = 0
         # Replay of a recorded step: the ~700 library calls of forward + loss + backward are recorded once per batch size
         # (backend.begin_record) and re-issued from the record afterwards, skipping this file's Python entirely -- at
@@ -185,12 +187,21 @@ class TrainEngine:
             self._gemm(dYt, ld, n_out, chunk, Xt, ld, k_out, out_f32=grad, ldo=k_out)
             return
         need = G * n_out * k_out
-        if self.partials is None or self.partials.numel() < need:
-            self.partials = self._f32(need)
+        # sized once per batch size in _alloc: a recorded step (tape / CUDA graph) keeps raw device pointers, so no buffer
+        # of the engine may be reallocated between _alloc calls
+        assert self.partials is not None and self.partials.numel() >= need, "split-K scratch undersized (see _dw_shapes)"
         self.be.gemm(dYt.hi, dYt.lo, Xt.hi, Xt.lo, n_out, k_out, chunk, groups=G, a_group=(G, chunk, 1, 0),
                      b_group=(G, chunk, 1, 0), a_rows=n_out, b_rows=k_out, lda=ld, ldb=ld, precision=self.precision,
                      out_f32=self.partials, ldo=k_out, group_rows=n_out)
         self.be.reduce_partials(self.partials, G, n_out * k_out, grad)
+
+    def _dw_shapes(self, B):
+        """(n_out, k_out, rows) of every weight-gradient contraction of one step (the calls of _dw in backward)"""
+        M, R, RJ, Ml = B * TOK, B * self.n_hm, B * self.J, B * self.live
+        shapes = [(PUH, PUH, RJ), (4 * PUH, PUH, RJ), (4 * PUH, PUX, RJ), (PUH + PUX, PUX, RJ)]
+        shapes += [(2048, 16 * HID, R), (2048, 8192, R), (512, 2048, R), (EMB, 512, R)]
+        shapes += [(HID, MLPD, M), (MLPD, HID, M), (HID, HID, M), (HID, 256, Ml)]
+        return shapes
 
     def _tsplit(self, src, rows, cols, src_ld, rm, t, t_ld, rows_in=0, rows_out=0, bias=None, gelu_u=None):
         """fp32 gradient -> row-major pair ``rm`` (rows x cols) and transposed pair ``t`` (cols x t_ld, zero padded);
@@ -336,8 +347,10 @@ class TrainEngine:
         S["bias_tmp"] = f32(5 * PUH)
         S["dpose"] = f32(B, self.nj, 3)
         self.x_in, self.gt_in = f32(B, 6 * J, 64, 64), f32(B, self.nj, 3)
+        self.partials = f32(max(splitk(n, k, r)[0] * n * k for n, k, r in self._dw_shapes(B)))
         self.batch = B
         self._tape = None
+        self._graph = self._graph_key = self._graph_warm = None      # recorded steps hold pointers into the old buffers
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, x):
@@ -348,6 +361,8 @@ class TrainEngine:
         self._alloc(B)
         if not self.packed:
             self.pack()
+        self.fwd_gen += 1
+        self.mutation += 1          # BatchNorm running buffers are updated below
         A, W = self.A, self.W
         M, R, RJ, live = B * TOK, B * self.n_hm, B * J, self.live
         v = "pos_heatmap_encoder.vit."
@@ -641,6 +656,7 @@ class TrainEngine:
             self.be.zero(self.opt_m)
             self.be.zero(self.opt_v)
         self.opt_step += 1
+        self.mutation += 1
         ks = self.order
         self.be.adamw([self.P[k] for k in ks], [self.grad[k] for k in ks],
                       [self.opt_m[self.offsets[k]:] for k in ks], [self.opt_v[self.offsets[k]:] for k in ks],

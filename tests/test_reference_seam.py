@@ -69,7 +69,7 @@ def test_reference_optimize_parameters_trains_our_module(tmp_path, state_dicts):
     model/egotap_autoencoder_model.py:299-323: .train(), zero_grad, forward, MPJPE + cos-sim losses, GradScaler,
     torch.optim.AdamW from model/network.py:72-78), driving OUR module through the swapped factory.  On CPU the module's
     training engine runs against the op oracle (tests only); the weights after one step must equal the training oracle's."""
-    import op_oracle
+    from oracle_backed import use_oracle_backend
     import train_oracle as tro
     import gt_heatmap_oracle as gto
     ref_shim.import_reference()
@@ -95,7 +95,7 @@ def test_reference_optimize_parameters_trains_our_module(tmp_path, state_dicts):
     net = model.net_AutoEncoder
     sd = state_dicts(preset)
     net.load_state_dict(sd, strict=True)
-    net._engine_backend = op_oracle.OracleBackend(exact=True)
+    use_oracle_backend(net)
     # one frame pair of ground-truth heatmaps (the --use_gt_heatmap path) and a target pose
     pts2d, pts3d = gto.synthetic_keypoints(preset, 2, seed=3)
     x = torch.stack([torch.from_numpy(gto.lifting_input(pts2d[b, 0], pts2d[b, 1], pts3d[b, 0], pts3d[b, 0], preset)) for b in range(2)])

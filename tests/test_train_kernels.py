@@ -49,9 +49,14 @@ def backends(request):
     yield GpuOpAdapter(), op_oracle.OracleBackend()
 
 
-def _default_schedule_only(backends):
-    if getattr(backends[0], "schedule", "emu") != "emu":
-        pytest.skip("engine-level / host-logic test: run once, on the default thread schedule")
+@pytest.fixture(scope="module")
+def emu_backends():
+    """the emulated-kernel backend on the default thread schedule (engine-level / host-logic tests run once, CPU only; their
+    hardware counterparts are tests/test_zz_train_gpu.py)"""
+    pair = build_emu.make_backend()
+    pair[0].name = "emu"
+    pair[0].schedule = "emu"
+    return pair
 
 
 def _pair(rows, cols, poison=True):
@@ -284,13 +289,10 @@ def test_head_bwd_embed_grads_loss_adamw(backends, preset, J, B):
             _same(x, y, 1e-5)
 
 
-def test_engine_on_emulated_kernels_matches_autograd(backends):
+def test_engine_on_emulated_kernels_matches_autograd(emu_backends):
     """the whole training step with every training op running on the emulated kernel source (GEMM / attention /
     LayerNorm / ingest / head from the oracle): gradients vs torch.autograd on the restated forward"""
-    emu, _ = backends
-    if emu.name != "emu":
-        pytest.skip("engine-level GPU parity lives in tests/test_zz_train_gpu.py")
-    _default_schedule_only(backends)
+    emu, _ = emu_backends
     preset, batch = "UnrealEgo", 1
     sd = weights.make_state_dict(preset, seed=5)
     params = {k: v.clone().contiguous() for k, v in sd.items()}
@@ -318,12 +320,10 @@ def test_engine_on_emulated_kernels_matches_autograd(backends):
         assert (upd - upd_ref).abs().max().item() <= 5e-2 * upd_ref.abs().max().item() + 2e-7, k
 
 
-def test_recorded_step_replays_identically(backends):
+def test_recorded_step_replays_identically():
     """TrainEngine records the library calls of one step and replays them afterwards (no Python orchestration on the
-    hot path): two steps (record, replay) must leave exactly the same weights as two steps without"""
-    if backends[0].name != "emu":
-        pytest.skip("host-side logic; the CUDA engine uses the same code path in tests/test_zz_train_gpu.py")
-    _default_schedule_only(backends)
+    hot path): two steps (record, replay) must leave exactly the same weights as two steps without.  Host-side logic; the CUDA
+    engine runs the same code path in tests/test_zz_train_gpu.py"""
     emu, _ = build_emu.make_backend(all_oracle=True)      # record / replay is host logic: ops served by the oracle
     preset, batch = "EgoCap", 1
     sd = weights.make_state_dict(preset, seed=5)

@@ -10,6 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import op_oracle
+from oracle_backed import use_oracle_backend
 import train_oracle as tro
 import weights
 from ref_shim import make_opt
@@ -20,7 +21,7 @@ def _module(preset, sd):
     import egotap_b200
     net = egotap_b200.EgoTAPAutoEncoder(make_opt(preset), input_channel_scale=2)
     net.load_state_dict(sd, strict=True)
-    net._engine_backend = op_oracle.OracleBackend(exact=True)
+    use_oracle_backend(net)
     return net
 
 
