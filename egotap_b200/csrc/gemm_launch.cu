@@ -98,11 +98,17 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
   GemmShape sh = s;
   if (sh.gdiv <= 0) sh.gdiv = int(a.g0_count > 0 ? a.g0_count : 1);
   ProfScope prof("gemm_tc_kernel", stream, s.M, s.N, s.K, s.groups, variant);
-  // EGOTAP_EPI=coalesced (opt-in, A/B): the epilogue that re-distributes each warp's chunk through shared memory so that
-  // its global accesses are coalesced (gemm.cuh); read per call so that one process can compare the two
-  const char* epi_env = getenv("EGOTAP_EPI");
-  if (epi_env && strcmp(epi_env, "coalesced") == 0) return v.launch_coalesced(tm, sh, ep, stream);
-  return v.launch(tm, sh, ep, stream);
+  // Epilogue form (gemm.cuh).  Measured on the B200 (profiles/r02_epilogue_ab.md): re-distributing each warp's chunk through
+  // shared memory pays where the epilogue touches fp32 rows (residual stream in / out: out-projection 533 -> 754 TFLOP/s in
+  // bf16 mode, patch embedding 152 -> 211) and costs where it only writes bf16 operands (MLP-up + GELU 889 -> 692: the
+  // extra shared-memory round trip lands on an epilogue that is already issue-bound).  EGOTAP_EPI=coalesced / rows forces
+  // one form for every GEMM (A/B runs); read per call so that one process can compare them.
+  bool coalesced = ep.resid != nullptr || ep.out_f32 != nullptr;
+  if (const char* epi_env = getenv("EGOTAP_EPI")) {
+    if (strcmp(epi_env, "coalesced") == 0) coalesced = true;
+    else if (strcmp(epi_env, "rows") == 0) coalesced = false;
+  }
+  return coalesced ? v.launch_coalesced(tm, sh, ep, stream) : v.launch(tm, sh, ep, stream);
 }
 
 }  // namespace eb

@@ -24,10 +24,6 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
                   int query_rows, cudaStream_t stream);
-// attention_wide.cu (EGOTAP_ATTN=wide: 128-key score tiles, P written over S in tensor memory)
-int attention_wide_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
-                       const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
-                       int query_rows, cudaStream_t stream);
 
 // pu_chain.cu
 int pu_permute_split_run(const float* W, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);

@@ -207,7 +207,7 @@ struct Plan {
     h0b = take2(w, B * J * PUH);
     FG1 = w.take<float>(B * J * 5 * PUH);
     skel = w.take<float>(B * J * PUH);
-    if (splitk_layout) {   // split-K partial products / sums of the first FC block at small batches (EGOTAP_SPLITK=1)
+    if (splitk_layout) {   // split-K partial products / sums of the first FC block at small batches (default; EGOTAP_SPLITK=0 disables)
       const size_t Bs = B < size_t(SPLITK_MAX_FRAMES) ? B : size_t(SPLITK_MAX_FRAMES);
       skp = w.take<float>(Bs * n_hm * 2048 * SPLITK_MAX_G);
       sky = w.take<float>(Bs * n_hm * 2048);
@@ -246,14 +246,16 @@ static bool fused_attention() {
   return v == 1;
 }
 
-// EGOTAP_SPLITK=1 (opt-in, unmeasured): at small batches the first FC block of both encoders (K = 16384 / 8192, only
-// B*2J rows) is a handful of tiles; cut its reduction dimension into G groups so that >= 128 CTAs stream the weight
-// matrix, sum the partial products and apply the folded BatchNorm + LeakyReLU in a separate bandwidth-bound pass
+// At small batches (<= 32 frames) the first FC block of both encoders (K = 16384 / 8192, only B*2J rows) is a handful of
+// tiles; its reduction dimension is cut into G groups so that >= 128 CTAs stream the weight matrix, the partial products are
+// summed and the folded BatchNorm + LeakyReLU applied in a separate bandwidth-bound pass.  Measured on the B200
+// (profiles/r02_small_batch.json): batch 1 1.59 -> 1.28 ms, batch 8 1.99 -> 1.69, batch 32 4.55 -> 4.43.  EGOTAP_SPLITK=0
+// turns it off (A/B check).
 static bool small_batch_splitk() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("EGOTAP_SPLITK");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }

@@ -19,6 +19,11 @@ def gather_poses(local_pose, total, group=None):
     world = dist.get_world_size(group)
     if world == 1:
         return local_pose
+    if total % world == 0:            # equal shards (the benchmarked case): one collective, no padding or re-assembly
+        assert local_pose.shape[0] == total // world
+        out = local_pose.new_empty((total,) + tuple(local_pose.shape[1:]))
+        dist.all_gather_into_tensor(out, local_pose.contiguous(), group=group)
+        return out
     sizes = [shard_bounds(total, world, r) for r in range(world)]
     biggest = max(hi - lo for lo, hi in sizes)
     pad = local_pose.new_zeros((biggest,) + tuple(local_pose.shape[1:]))
@@ -27,6 +32,18 @@ def gather_poses(local_pose, total, group=None):
     dist.all_gather_into_tensor(out, pad, group=group)
     out = out.view((world, biggest) + tuple(local_pose.shape[1:]))
     return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+def gather_job_poses(local_poses, group=None):
+    """The final gather of a sharded JOB: every rank has run its own K batches of B_local frames with no collective in
+    between and holds ``(K, B_local, num_joints, 3)`` poses; all ranks receive ``(world, K, B_local, num_joints, 3)``
+    (rank-major, equal shards).  One collective per job instead of one per batch: ranks never wait for each other while
+    they compute, so per-step rank skew (power capping) does not accumulate into the job time."""
+    world = dist.get_world_size(group)
+    local_poses = local_poses.contiguous()
+    out = local_poses.new_empty((world * local_poses.shape[0],) + tuple(local_poses.shape[1:]))
+    dist.all_gather_into_tensor(out, local_poses, group=group)         # rank-major concatenation along dim 0
+    return out.view((world,) + tuple(local_poses.shape))
 
 
 class ShardedLifter:

@@ -18,7 +18,8 @@ import sys
 import types
 from types import SimpleNamespace
 
-REF_CANDIDATES = [os.environ.get("EGOTAP_REF", ""), "/root/reference"]
+REF_CANDIDATES = [os.environ.get("EGOTAP_REF", ""), "/root/reference",
+                  os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
 
 
 def reference_root():

@@ -18,7 +18,7 @@ def pytest_configure(config):
 # test is an ordinary strict test (round 1's non-strict first-hardware-run quarantine is gone: all of it passed on the B200).
 _GPU_FILE_ORDER = ["test_gemm_gpu.py", "test_ops_gpu.py", "test_lifting_gpu.py", "test_metrics.py", "test_heatmap_net.py",
                    "test_gt_heatmaps.py", "test_train_kernels.py", "test_zz_train_gpu.py", "test_zzz_graph_inference_gpu.py",
-                   "test_zzz_attention_wide_gpu.py", "test_zzz_epilogue_coalesced_gpu.py"]
+                   "test_zzz_epilogue_coalesced_gpu.py"]
 
 
 # CPU tests that run in a background child process started with their module (tests/test_tensorcore_emu.py): collected last

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "egotap_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
 SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(HERE, "selftest.cu"), os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "gemm_launch.cu"),
-           os.path.join(CSRC, "attention.cu"), os.path.join(CSRC, "attention_wide.cu"), os.path.join(CSRC, "pu_chain.cu"), os.path.join(CSRC, "pu_chain_bwd.cu"), os.path.join(CSRC, "metrics.cu"),
+           os.path.join(CSRC, "attention.cu"), os.path.join(CSRC, "pu_chain.cu"), os.path.join(CSRC, "pu_chain_bwd.cu"), os.path.join(CSRC, "metrics.cu"),
            os.path.join(CSRC, "plan.cu"),
            os.path.join(CSRC, "train_ops.cu"),
            os.path.join(CSRC, "train_model.cu"),

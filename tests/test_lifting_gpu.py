@@ -93,9 +93,14 @@ def test_stages_match_oracle(preset, precision, tol, state_dicts):
     torch.cuda.synchronize()
     rep.update({"pose_" + k: v for k, v in orc.parity_report(pose, ref_pose).items()})
     _record("stages_%s_%s" % (preset, precision), rep)
-    bad = {k: v for k, v in rep.items() if k not in ("pose_max_abs_mm", "pose_mpjpe_delta_mm") and not (v <= tol)}
+    unscaled = ("pose_max_abs_mm", "pose_mpjpe_delta_mm", "pose_per_joint_rel", "pose_joints_counted", "pose_joints_total")
+    bad = {k: v for k, v in rep.items() if k not in unscaled and not (v <= tol)}
     assert not bad, (bad, rep)
     assert rep["pose_mpjpe_delta_mm"] <= (0.01 if precision == "bf16x3" else 0.5), rep
+    # BASELINE.json north_star: "per-joint 3D coordinates within 1e-3 relative" (fp32-accumulate mode); the bf16-operand mode
+    # has its own stated bound: 5e-2 of the batch maximum (tol above) and 1e-1 per joint
+    assert rep["pose_per_joint_rel"] <= (1e-3 if precision == "bf16x3" else 1e-1), rep
+    assert rep["pose_joints_counted"] >= 0.9 * rep["pose_joints_total"], rep
 
 
 @pytest.mark.parametrize("preset", ["UnrealEgo", "EgoCap"])
@@ -110,7 +115,7 @@ def test_matches_reference_golden(preset, kind, state_dicts):
     pose, rot, indep, hm = net(x)
     rep = orc.parity_report(pose, torch.from_numpy(gold["pose"]))
     _record("golden_%s_%s" % (preset, kind), rep)
-    assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01, rep
+    assert rep["rel"] <= 5e-4 and rep["mpjpe_delta_mm"] <= 0.01 and rep["per_joint_rel"] <= 1e-3, rep
     # quirks that are specification: 4-tuple of the reference's shapes, aux outputs all zero, head joint last
     assert [rot.shape[1], indep.shape[1], hm.shape[1]] == list(gold["aux_shapes"]) and hm.shape == x.shape
     assert rot.abs().max() == 0 and indep.abs().max() == 0 and hm.abs().max() == 0
@@ -133,22 +138,25 @@ def test_batch_sizes_and_ragged_batches(state_dicts):
     assert orc.parity_report(full, ref)["rel"] <= 5e-4
 
 
-def test_full_size_batch_equals_small_batches(state_dicts):
+@pytest.mark.parametrize("preset,precision,tol", [("UnrealEgo", "bf16x3", 5e-4), ("EgoCap", "bf16", 5e-2)])
+def test_full_size_batch_equals_small_batches(preset, precision, tol, state_dicts):
     """BASELINE.json's full sizes through a size-independent property: frames are independent, so a batch of 1100
     (more than one 1024-frame chunk of the persistent chain kernel, several waves of every GEMM) must reproduce,
-    row for row, what the same frames give in batches of 256 / 76 -- which the oracle tests pin at small size."""
+    row for row, what the same frames give in batches of 256 / 76 -- which the oracle tests pin at small size.
+    Cases: config 2's preset / precision, and config 3's (EgoCap, bf16 operands, batch >= 1024)."""
     from egotap_b200 import synthetic_heatmaps
-    preset = "UnrealEgo"
-    net = _module(preset, "bf16x3", state_dicts(preset))
+    net = _module(preset, precision, state_dicts(preset))
     base = synthetic_heatmaps(preset, 44, seed=21, kind="gauss").cuda()
     x = base.repeat(25, 1, 1, 1) * torch.linspace(0.5, 1.5, 1100, device="cuda")[:, None, None, None]
     big = net.predict_pose(x).clone()
     parts = torch.cat([net.predict_pose(x[i:i + 256]).clone() for i in range(0, 1024, 256)] + [net.predict_pose(x[1024:]).clone()])
     assert torch.isfinite(big).all()
-    assert (big - parts).abs().max().item() < 2e-5
+    assert (big - parts).abs().max().item() < 2e-5 * max(1.0, big.abs().max().item())
     with torch.no_grad():
-        ref = orc.forward(state_dicts(preset), x[1098:].cpu(), preset)
-    assert orc.parity_report(big[1098:], ref)["rel"] <= 5e-4
+        ref = orc.forward(state_dicts(preset), x[1084:].cpu(), preset)
+    rep = orc.parity_report(big[1084:], ref)                      # 16 frames of the last (ragged) chunk vs the oracle
+    _record("full_size_%s_%s" % (preset, precision), rep)
+    assert rep["rel"] <= tol, rep
 
 
 def test_per_joint_launch_path_agrees_with_persistent_chain(state_dicts):

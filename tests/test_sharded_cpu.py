@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from egotap_b200.sharded import ShardedLifter, gather_poses, shard_bounds
+from egotap_b200.sharded import ShardedLifter, gather_job_poses, gather_poses, shard_bounds
 
 
 def test_shard_bounds_cover_exactly():
@@ -40,7 +40,13 @@ def _worker(rank, world, port, total, q):
         got = ShardedLifter(_FakeNet()).predict_pose(frames)
         lo, hi = shard_bounds(total, world, rank)
         got2 = ShardedLifter(_FakeNet()).predict_pose(frames[lo:hi], total=total, presharded=True)
-        q.put((rank, bool(torch.equal(got, want)), bool(torch.equal(got2, want))))
+        # a sharded JOB: K batches per rank with no collective in between, one gather at its end (bench.py --gpus N)
+        K, Bl = 3, 2
+        mine = torch.stack([_FakeNet().predict_pose(frames[:Bl] + 10 * rank + k) for k in range(K)])
+        job = gather_job_poses(mine)
+        job_ok = tuple(job.shape) == (world, K, Bl, 16, 3) and all(
+            torch.equal(job[r, k], _FakeNet().predict_pose(frames[:Bl] + 10 * r + k)) for r in range(world) for k in range(K))
+        q.put((rank, bool(torch.equal(got, want)), bool(torch.equal(got2, want)) and job_ok))
     finally:
         dist.destroy_process_group()
 

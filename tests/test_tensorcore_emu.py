@@ -161,7 +161,7 @@ def test_coalesced_epilogue_variant(be):
     bh, bl = _pairs(b)
     bias, h0 = torch.randn(N), torch.randn(M, N)
     outs = []
-    for mode in ("", "coalesced"):
+    for mode in ("rows", "coalesced"):
         h = h0.clone()
         hi, lo = torch.full((M, N), float("nan"), dtype=BF16), torch.full((M, N), float("nan"), dtype=BF16)
         with _env("EGOTAP_EPI", mode):
@@ -233,7 +233,7 @@ def test_gemm_grouped_operands(be, variant, prec):
 
 
 @pytest.mark.parametrize("prec", [1, 0])
-@pytest.mark.parametrize("variant", ["", "wide"])
+@pytest.mark.parametrize("variant", [""])
 def test_fused_attention_kernel(be, prec, variant):
     """14 warps, ten mbarrier families, S and O double-buffered in tensor memory, P as the TS-form A operand, lazy rescale;
     2 frames = 80 work items on the emulated 6-SM device, i.e. ~13 items per persistent CTA (phase parities wrap).

@@ -40,7 +40,7 @@ net = net.cuda().eval()
 x = egotap_b200.synthetic_heatmaps(preset, batch, seed=8)
 os.environ["EGOTAP_EPI"] = "coalesced"
 coal = net.predict_pose(x.cuda()).clone(); torch.cuda.synchronize()
-os.environ.pop("EGOTAP_EPI")
+os.environ["EGOTAP_EPI"] = "rows"
 base = net.predict_pose(x.cuda()).clone(); torch.cuda.synchronize()
 with torch.no_grad():
     ref = orc.forward(sd, x[:4], preset)

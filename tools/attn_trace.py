@@ -8,7 +8,7 @@ import glob
 _csrc = glob.glob(os.path.join(ROOT, "egotap_b200", "csrc", "*"))
 if not os.path.isfile(lib) or "--build" in sys.argv or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in _csrc):
     os.makedirs(os.path.dirname(lib), exist_ok=True)
-    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "attention_wide.cu", "pu_chain.cu", "pu_chain_bwd.cu",
+    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "pu_chain_bwd.cu",
                                                                        "metrics.cu", "plan.cu", "train_ops.cu", "train_model.cu", "gt_heatmap.cu")]
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
                            "-DEB_ATTN_TRACE", "-o", lib] + src)
