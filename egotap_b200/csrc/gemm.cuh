@@ -86,27 +86,35 @@ __device__ __forceinline__ void epi_load_resid(const EpiParams& p, const EpiRow&
   for (int j = 0; j < 8; ++j) t[j] = r4[j];
 }
 
-__device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
-                                          const float4 (&t)[8]) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+// Per-column vectors of the epilogue (folded scale, bias) for the 32 columns of a chunk.  They are staged once per tile in
+// shared memory by the epilogue threads (one column each, requested BEFORE the accumulator wait) and read back as warp-wide
+// broadcasts: the first version fetched them with __ldg inside the chunk loop, and the first use of every chunk sat on that
+// L2 round trip (ncu, bf16 mode: 13-17 % of all samples of the QKV / MLP-up GEMMs on the first bias FADD of a chunk).
+__device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* sv_scale, const float* sv_bias, float (&v)[32]) {
   if (p.scale) {
-    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
+    const float4* s4 = reinterpret_cast<const float4*>(sv_scale);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 s = __ldg(s4 + j);
+      const float4 s = s4[j];
       v[4 * j] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
     }
   }
   if (p.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+    const float4* b4 = reinterpret_cast<const float4*>(sv_bias);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
+      const float4 b = b4[j];
       v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
     }
   }
+}
+
+__device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
+                                          const float4 (&t)[8], const float* sv_scale, const float* sv_bias) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  epi_scale_bias(p, sv_scale, sv_bias, v);
   if (p.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -200,26 +208,12 @@ __device__ __forceinline__ void epi_load_resid_t(const EpiParams& p, const EpiRo
   }
 }
 __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const EpiRow& row, const EpiRowsT& rows, int n0,
-                                                    uint32_t (&r)[32], const float4 (&t)[8], float4* stg, int lane) {
+                                                    uint32_t (&r)[32], const float4 (&t)[8], float4* stg, int lane,
+                                                    const float* sv_scale, const float* sv_bias) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-  if (p.scale) {
-    const float4* s4 = reinterpret_cast<const float4*>(p.scale + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 s = __ldg(s4 + j);
-      v[4 * j] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
-    }
-  }
-  if (p.bias) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
-      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-    }
-  }
+  epi_scale_bias(p, sv_scale, sv_bias, v);
   if (p.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -265,12 +259,16 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
   static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+  static constexpr int VEC_BYTES = 2 * BN * 4;       // the tile's columns of the epilogue scale / bias vectors
   static constexpr int STG_BYTES = COAL ? EPI_WARPS * 4096 : 0;   // coalesced epilogue: one 32 x 32 fp32 block per warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // + alignment slack
+  static constexpr int VEC_OFF = STAGES * STAGE_BYTES + BAR_BYTES;
+  static constexpr int STG_OFF = VEC_OFF + VEC_BYTES;
+  static constexpr int SMEM_BYTES = STG_OFF + STG_BYTES;           // the dynamic shared memory is declared 1 KB aligned
   static constexpr int COLS_PER_EPI_GROUP = BN / (EPI_WARPS / 4);
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(BN == 32 * EPI_WARPS, "one epilogue thread per tile column (staging of the scale / bias vectors)");
 };
 
 template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false>
@@ -279,8 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
   using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL>;
-  EB_DYN_SMEM(smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  EB_DYN_SMEM_1K(smem);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -391,13 +389,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;
     const int col_base = ((warp - 2) >> 2) * C::COLS_PER_EPI_GROUP;
+    const int et = int(threadIdx.x) - 64;          // epilogue thread = the tile column whose scale / bias it stages
+    float* sv_scale = reinterpret_cast<float*>(smem + C::VEC_OFF);
+    float* sv_bias = sv_scale + BN;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int n_blk = tile % nN; const int t2 = tile / nN;
       const int m_blk = t2 % nM;   const int g = t2 / nM;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      {
+        // this tile's columns of the scale / bias vectors: requested before the accumulator wait, staged in shared memory
+        const int ncol = n_blk * BN + et;
+        float my_scale = 1.0f, my_bias = 0.0f;
+        if (ep.scale != nullptr && ncol < s.N) my_scale = __ldg(ep.scale + ncol);
+        if (ep.bias != nullptr && ncol < s.N) my_bias = __ldg(ep.bias + ncol);
+        named_bar_sync<32 * C::EPI_WARPS>(1);      // every epilogue warp has finished reading the previous tile's vectors
+        sv_scale[et] = my_scale;
+        sv_bias[et] = my_bias;
+      }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      named_bar_sync<32 * C::EPI_WARPS>(1);        // staged vectors visible to all epilogue warps
       const int m = m_blk * C::BM * CG + cta_rank * C::BM + q * 32 + lane;
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
       const bool row_ok = m < s.M;
@@ -407,8 +419,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const int n_first = n_blk * BN + col_base;
       if constexpr (COAL) {
         // transposed-domain epilogue (see epi_apply_coalesced); the transposed V store of STORE_QKV keeps the row-domain path
-        float4* stg = reinterpret_cast<float4*>(smem + STAGES * C::STAGE_BYTES + C::BAR_BYTES) + (warp - 2) * 256;
+        float4* stg = reinterpret_cast<float4*>(smem + C::STG_OFF) + (warp - 2) * 256;
         const EpiRowsT rows = epi_rows_t(row, row_ok, lane);
+        // coalesced residual loads run ONE CHUNK AHEAD of the math (ncu, bf16 mode: with the loads issued in the chunk that
+        // uses them, 22 % of the out-projection's samples sat on the first residual FADD of a chunk)
+        const bool has_resid = ep.resid != nullptr && ep.store != STORE_QKV;
+        if (has_resid && n_first < s.N) epi_load_resid_t(ep, row, rows, n_first, lane, t_cur);
 #pragma unroll 1
         for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
           const int n0 = n_first + c * 32;
@@ -416,13 +432,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const bool v_part = ep.store == STORE_QKV && n0 >= ep.qk_cols;
           uint32_t r[32];
           tmem_ld32(t_addr + col_base + c * 32, r);
-          // coalesced residual loads of this chunk, in flight across the TMEM wait, the pointwise math and the staging
-          if (ep.resid != nullptr && !v_part) epi_load_resid_t(ep, row, rows, n0, lane, t_cur);
+          const bool more = (c + 1 < C::COLS_PER_EPI_GROUP / 32) && (n0 + 32 < s.N);
+          if (has_resid && more) epi_load_resid_t(ep, row, rows, n0 + 32, lane, t_nxt);
           tmem_ld_wait();
+          const float* svs = sv_scale + col_base + c * 32;
+          const float* svb = sv_bias + col_base + c * 32;
           if (v_part) {
-            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur);
+            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, svs, svb);
           } else {
-            epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane);
+            epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane, svs, svb);
+          }
+          if (has_resid && more) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];
           }
         }
         tc_fence_before();
@@ -442,7 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const bool more = (c + 1 < C::COLS_PER_EPI_GROUP / 32) && (n0 + 32 < s.N);
         if (use_resid && more) epi_load_resid(ep, row, n0 + 32, t_nxt);   // prefetch the next chunk's residual
         tmem_ld_wait();
-        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur);
+        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32);
         if (use_resid && more) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];

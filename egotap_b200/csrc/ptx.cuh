@@ -80,10 +80,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on the barrier at the same smem offset in cluster CTA `cta`
+// arrive on the barrier at the same smem offset in cluster CTA `cta`.  Default semantics (no explicit .release.cluster): the
+// only use is "this warp has drained its accumulator buffer", ordered by tcgen05.fence::before_thread_sync + tcgen05.wait::ld;
+// nothing written to global memory is published through it.  The .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in
+// front of the arrive, i.e. every epilogue warp waited for ALL its outstanding global stores once per tile (measured with ncu
+// on the B200, profiles/r02_gemm_bf16_ncu.md: 8-12 % of the samples of the cta_group::2 GEMMs sat on that fence).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(bar), cta))
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa(smem_u32(bar), cta)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -257,10 +257,42 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   }
 }
 
+// Tall reductions (G in the thousands, n a few thousand: the per-tile column sums behind every bias gradient): one thread per
+// output element would leave ~1 k threads walking 2 k rows each (measured on the B200: 0.47 ms for 2304 x 4096 floats = 80 GB/s).
+// Here a CTA owns 64 output floats and its 16 row lanes walk the G rows interleaved; the 16 lane sums are folded in a fixed
+// order (deterministic), so n / 64 CTAs x 256 threads stream the partials.
+__global__ void __launch_bounds__(256) reduce_partials_tall_kernel(const float* __restrict__ p, int G, long long n4,
+                                                                   float* __restrict__ out) {
+  __shared__ float4 part[16][16];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const long long i = (long long)blockIdx.x * 16 + cl;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    for (int g = rl; g < G; g += 16) {
+      const float4 v = reinterpret_cast<const float4*>(p)[(long long)g * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0 && i < n4) {
+    for (int r = 1; r < 16; ++r) {
+      const float4 v = part[r][cl];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 int reduce_partials_run(const float* partials, int G, long long n, float* out, cudaStream_t st) {
   EB_REQUIRE(partials && out && G >= 1 && n > 0 && n % 4 == 0, "reduce_partials: bad arguments (G %d n %lld)", G, n);
   ProfScope prof("reduce_partials_kernel", st);
-  EB_LAUNCH(reduce_partials_kernel, (blocks_for(n / 4, 256, 148 * 8)), 256, st, partials, G, n / 4, out);
+  const long long n4 = n / 4;
+  if (G >= 64 && n4 <= 148 * 8 * 256 / 4) {       // tall and narrow: the flat kernel would not fill the machine
+    EB_LAUNCH_COOP(reduce_partials_tall_kernel, (unsigned)((n4 + 15) / 16), 256, st, partials, G, n4, out);
+  } else {
+    EB_LAUNCH(reduce_partials_kernel, (blocks_for(n4, 256, 148 * 8)), 256, st, partials, G, n4, out);
+  }
   EB_CHECK_LAUNCH("reduce_partials_kernel");
   return 0;
 }

@@ -139,6 +139,10 @@ def test_colsum_and_reduce_partials(backends, rows, cols, rows_in, rows_out):
     part = torch.randn(5, 1024)
     a, b = _both(backends, "reduce_partials", lambda: [part, 5, 1024, torch.zeros(1024)])
     _same(a[3], b[3], 1e-6)
+    # tall and narrow (the column sums behind a bias gradient: thousands of per-tile rows): the 16-row-lane kernel, ragged n
+    tall = torch.randn(203, 1000)
+    a, b = _both(backends, "reduce_partials", lambda: [tall, 203, 1000, torch.full((1000,), float("nan"))])
+    _same(a[3], b[3], 5e-6)
 
 
 def test_gelu(backends):
