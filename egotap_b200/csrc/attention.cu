@@ -5,7 +5,15 @@
 // ~55 cycles the issuing warp needs per tcgen05.mma (measured), with ~40 mbarrier round trips per work item; it ran at 50.6 %
 // tensor-pipe activity (1.058 ms per layer at batch 256, parity mode) and was deleted in round 2 when this structure measured
 // 65.7 % / 0.994 ms (0.484 vs 0.523 ms in bf16 mode; profiles/r02_attention_ab.md).  Here every MMA is 128 x 128 x 16
-// (64 cycles of math) and the hand-offs are cut to ~26 per item:
+// (64 cycles of math) and the hand-offs are cut to ~26 per item.
+//
+// Measured limits of this structure (round 2, profiles/r02c_attention_analysis.md): per 128-key tile the tensor pipe needs
+// 3,072 cycles in the parity mode (1,024 in bf16 mode) and the period is T_PV + max(T_S, T_softmax) with T_softmax ~ 3,100
+// cycles for the 8 softmax warps -- ~50 cycles per score element and thread, set by tcgen05.ld / tcgen05.st round trips
+// that share the tensor-memory ports with the running MMAs, not by MUFU (XU pipe 20 % busy) or issue slots (29 %).  A variant
+// with two softmax groups alternating over the tiles (one query row per thread, no intra-tile exchange, epilogue folded into
+// the groups) was built, verified and timed: 1.016 / 0.503 ms vs 0.994 / 0.484 ms here (parity / bf16, batch 256) -- the
+// per-element cost did not change, so the longer per-tile chain of a 4-warp group cancelled the overlap.  It was dropped.
 //   * 128-key score tiles (576 keys = 4 full tiles + one 64-key tile, issued with N = 64);
 //   * P_g is written over the columns of S_g (same tensor-memory buffer: S 128 fp32 columns -> P 64 hi + 64 lo packed
 //     bf16x2 columns), so TMEM holds S/P 2 x 128 + O 2 x 128 = 512 columns;
@@ -18,9 +26,8 @@
 //     while the softmax warps finish the current item.
 // Shared memory: Q tile (hi/lo; two of them in bf16 mode) + a ring of 32 KB granules (one 64-wide d block of a 128-key K tile, or one 64-key
 // block of a V^T tile), consumed in MMA order.
-//   warp 0   TMA producer      warp 1   MMA issuer
-//   warps 2-5 / 6-9  two softmax groups alternating over the tiles (one query row per thread, running concurrently on
-//   consecutive tiles); the group that finishes an item also turns O (double-buffered across items) / l into context rows
+//   warp 0   TMA producer      warp 1   MMA issuer      warps 2-9  softmax (pairs split the keys of a tile)
+//   warps 10-13  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
 #include "gemm.cuh"
 #include "host_util.cuh"
 #include "internal.h"
@@ -42,7 +49,7 @@ __device__ unsigned long long g_attn_trace[32];
 constexpr int AW_TOK = 576, AW_HEADS = 8, AW_D = 128, AW_QT = 128, AW_KT = 128;
 constexpr int AW_NT = (AW_TOK + AW_KT - 1) / AW_KT;          // 5 key tiles, the last one has 64 keys
 constexpr int AW_LAST_KEYS = AW_TOK - (AW_NT - 1) * AW_KT;   // 64
-constexpr int AW_THREADS = 64 + 256;                         // TMA + MMA warps, 2 softmax groups of 4 warps
+constexpr int AW_THREADS = 64 + 256 + 128;                   // TMA + MMA warps, 8 softmax warps, 4 epilogue warps
 static_assert(AW_LAST_KEYS == 64, "the last key tile is issued with N = 64");
 
 template <int NSPLIT>
@@ -56,13 +63,13 @@ struct AttnWideCfg {
   // buffer is reloaded when the item's last score tile has been computed; the tile is prefetched into L2 an item ahead.
   static constexpr int QBUF = NSPLIT == 1 ? 2 : 1;
   static constexpr int BAR_OFF = QBUF * Q_BYTES + NSLOTS * GRAN_BYTES;
-  static constexpr int XCHG_OFF = BAR_OFF + 512;             // [4][128] reference maxima (slot = tile & 3), then [2][128] partial row sums
+  static constexpr int XCHG_OFF = BAR_OFF + 256;             // [2][2][128] row maxima, then [2][2][128] row sums
   static constexpr int SMEM_BYTES = XCHG_OFF + 4096;         // base must be 1 KB aligned (checked)
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
   static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(2 * QBUF + 2 * NSLOTS + 16 + 1 <= 64, "barrier block");
+  static_assert(2 * QBUF + 2 * NSLOTS + 10 + 1 <= 32, "barrier block");
 };
 
 template <int NSPLIT>
@@ -85,11 +92,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
   uint64_t* pv_done = p_full + 2;           // [2]  PV_g finished: O up to date (needed only for a rescale of O)
   uint64_t* o_full = pv_done + 2;           // [2]  last PV of an item finished
   uint64_t* o_empty = o_full + 2;           // [2]  epilogue has drained that O buffer
-  uint64_t* mref_full = o_empty + 2;        // [4]  reference maximum after tile g published (slot g & 3)
-  uint64_t* lpart_full = mref_full + 4;     // [2]  partial row sums of the group that does NOT finish the item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lpart_full + 2);
-  float* mref_s = reinterpret_cast<float*>(smem + C::XCHG_OFF);   // [4][128]
-  float* lpart = mref_s + 512;                                     // [2][128]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  float* xmax = reinterpret_cast<float*>(smem + C::XCHG_OFF);     // [2][2][128]
+  float* lsum = xmax + 512;                                        // [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_items = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // grid <= num_items
@@ -103,10 +108,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
     for (int i = 0; i < C::QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&lpart_full[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&mref_full[i], 4);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
@@ -268,151 +272,141 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       issue_pv(g);
     }
     TW_FLUSH(0, lane == 0)
-  } else {
-    // ------------------------------------------------------------------ softmax groups (2 x 4 warps)
-    // Group 0 = warps 2-5 owns the even global tiles (S/P buffer 0), group 1 = warps 6-9 the odd ones (buffer 1); every
-    // thread owns one query row of its group's tile (the four warps of a group cover the four TMEM lane quarters) and holds
-    // the whole score row in registers, so there is no intra-tile exchange.  The two groups work on consecutive tiles
-    // CONCURRENTLY: the softmax of tile g+1 starts as soon as S_{g+1} is in tensor memory, while the other group is still
-    // exponentiating tile g -- the issuing warp only ever waits for a P tile if one softmax takes longer than a whole
-    // S + PV step of the tensor pipe.  What couples the groups is the running reference maximum of a row: the group of
-    // tile g publishes it (m_ref[g & 3]) right after its max pass, the group of tile g+1 picks it up after its own.
-    // Each group keeps a partial row sum in the scale of the reference it last saw; the group that processes an item's
-    // last tile adds the other group's partial (published after tile NT-2), waits for the last PV and drains O.
-    const int grp = (warp - 2) >> 2;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ softmax warps (8)
+    // Warps w and w+4 own the same TMEM lane quarter (query rows) and split the keys of a tile into two halves; the
+    // pair agrees on the row maximum through shared memory and a 64-thread named barrier -- which also separates the
+    // pair's loads of S from its stores of P into the same columns.
     const int q = warp & 3;                       // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;               // key half handled by this warp
     const int row = q * 32 + lane;                // query row inside the tile
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
-    const uint32_t t_s = C::T_S + uint32_t(grp) * 128u + lane_sel;
     const float c = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
-    float m_own = 0.f, l = 0.f;
+    float m_ref = 0.f, l = 0.f;
     TW_DECL
 #pragma unroll 1
-    for (int g = grp; g < my_tiles; g += 2) {
+    for (int g = 0; g < my_tiles; ++g) {
       const int it = g / AW_NT, j = g % AW_NT;
-      const uint32_t par = uint32_t(g >> 1) & 1u;
+      const uint32_t sb = uint32_t(g & 1), par = uint32_t(g >> 1) & 1u;
+      const uint32_t t_s = C::T_S + sb * 128u + lane_sel;
       const uint32_t t_o = C::T_O + uint32_t(it & 1) * AW_D + lane_sel;
-      const bool full_tile = j != AW_NT - 1;      // 128 keys, or 64 in the last tile
-      const bool first = j < 2;                   // this group's first tile of the item
-      TW_WAIT(1, mbar_wait(&s_full[grp], par));
+      const bool full_tile = j != AW_NT - 1;      // this warp: 64 keys of a full tile, 32 of the last one
+      const uint32_t col0 = full_tile ? hf * 64 : hf * 32;
+      if (j == 0) l = 0.f;
+      TW_WAIT(1, mbar_wait(&s_full[sb], par));
       tc_fence_after();
-      uint32_t r[4][32];
-      tmem_ld32(t_s, r[0]);
-      tmem_ld32(t_s + 32, r[1]);
-      if (full_tile) { tmem_ld32(t_s + 64, r[2]); tmem_ld32(t_s + 96, r[3]); }
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_s + col0, r0);
+      if (full_tile) tmem_ld32(t_s + col0 + 32, r1);
       tmem_ld_wait();
-      float mt;
-      {
-        float a0 = __uint_as_float(r[0][0]), a1 = __uint_as_float(r[0][1]), a2 = __uint_as_float(r[1][0]),
-              a3 = __uint_as_float(r[1][1]);
+      float mt = __uint_as_float(r0[0]);
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) {
-          a0 = fmaxf(a0, __uint_as_float(r[0][i])); a1 = fmaxf(a1, __uint_as_float(r[0][i + 1]));
-          a2 = fmaxf(a2, __uint_as_float(r[1][i])); a3 = fmaxf(a3, __uint_as_float(r[1][i + 1]));
-        }
-        if (full_tile) {
+      for (int i = 1; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(r0[i]));
+      if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            a0 = fmaxf(a0, __uint_as_float(r[2][i])); a1 = fmaxf(a1, __uint_as_float(r[2][i + 1]));
-            a2 = fmaxf(a2, __uint_as_float(r[3][i])); a3 = fmaxf(a3, __uint_as_float(r[3][i + 1]));
-          }
-        }
-        mt = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(r1[i]));
       }
-      // reference maximum of the row after the previous tile of this item (the other group's tile)
-      float m_prev = mt;
-      if (j > 0) {
-        TW_WAIT(2, mbar_wait(&mref_full[(g - 1) & 3], uint32_t((g - 1) >> 2) & 1u));
-        m_prev = mref_s[((g - 1) & 3) * 128 + row];
-      }
-      if (first) { l = 0.f; }
-      else if (m_own != m_prev) { l *= ex2_approx((m_own - m_prev) * c); }     // the other group raised the reference
-      const bool need = (j > 0) && ((mt - m_prev) * c > 8.0f);
-      float f = 1.0f, m_new = m_prev;
-      if (need) { f = ex2_approx((m_prev - mt) * c); m_new = mt; l *= f; }
-      m_own = m_new;
-      mref_s[(g & 3) * 128 + row] = m_new;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mref_full[g & 3]);
-      const float mc = m_new * c;
-      if (__any_sync(0xffffffffu, need)) {        // lazy rescale of this row's O: needs PV_{g-1} complete
-        TW_WAIT(3, mbar_wait(&pv_done[grp ^ 1], uint32_t((g - 1) >> 1) & 1u));
+      float* xm = xmax + (g & 1) * 256;
+      xm[hf * 128 + row] = mt;
+      tc_fence_before();
+      TW_WAIT(2, named_bar_sync<64>(1 + q));
+      tc_fence_after();
+      mt = fmaxf(mt, xm[(hf ^ 1) * 128 + row]);
+      if (j == 0) m_ref = mt;
+      const bool need = (j > 0) && ((mt - m_ref) * c > 8.0f);
+      float f = 1.0f;
+      if (need) { f = ex2_approx((m_ref - mt) * c); m_ref = mt; l *= f; }
+      const float mc = m_ref * c;
+      if (__any_sync(0xffffffffu, need)) {        // lazy rescale of this warp's 64 O columns: needs PV_{g-1} complete
+        TW_WAIT(3, mbar_wait(&pv_done[sb ^ 1], uint32_t((g - 1) >> 1) & 1u));
         tc_fence_after();
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t o[32];
-          tmem_ld32(t_o + ch * 32, o);
+          tmem_ld32(t_o + hf * 64 + ch * 32, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-          tmem_st32(t_o + ch * 32, o);
+          tmem_st32(t_o + hf * 64 + ch * 32, o);
         }
       }
-      // probabilities: 32 keys = 16 packed columns per chunk, written over S (hi at [0,64), lo at [64,128)); the whole
-      // score row is in registers, so the stores cannot run over scores that are still to be read
+      // probabilities: 32 keys = 16 packed columns per chunk, written over S (hi at [0,64), lo at [64,128))
+      const uint32_t pcol0 = full_tile ? hf * 32 : hf * 16;
+      {
+        uint32_t hh[16], ll[16];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < 2 || full_tile) {
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r0[2 * e]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r0[2 * e + 1]), c, -mc));
+          l += p0 + p1;
+          if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + pcol0, hh);
+        if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0, ll);
+      }
+      if (full_tile) {
+        uint32_t hh[16], ll[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r1[2 * e]), c, -mc));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r1[2 * e + 1]), c, -mc));
+          l += p0 + p1;
+          if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + pcol0 + 16, hh);
+        if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0 + 16, ll);
+      }
+      tmem_st_wait();
+      if (j == AW_NT - 1) lsum[(it & 1) * 256 + hf * 128 + row] = l;   // for the epilogue warps, ordered by p_full
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+    }
+    TW_FLUSH(8, warp == 2 && lane == 0)
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (4): O / l -> ctx rows
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = uint32_t(q * 32) << 16;
+    int it = 0;
+    TW_DECL
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qt = item % qtiles, bh = item / qtiles;
+      const int h = bh % AW_HEADS, b = bh / AW_HEADS;
+      const int ob = it & 1;
+      TW_WAIT(1, mbar_wait(&o_full[ob], (it >> 1) & 1));
+      tc_fence_after();
+      const float inv = 1.0f / (lsum[ob * 256 + row] + lsum[ob * 256 + 128 + row]);
+      const int tok = qt * AW_QT + row;
+      const long long orow = (long long)b * AW_TOK + tok;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(C::T_O + ob * AW_D + lane_sel + ch * 32, o);
+        tmem_ld_wait();
+        if (tok < AW_TOK) {
           uint32_t hh[16], ll[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[k][2 * e]), c, -mc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[k][2 * e + 1]), c, -mc));
-            l += p0 + p1;
-            if (NSPLIT > 1) split_pack2(p0, p1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(p0, p1);
+            const float v0 = __uint_as_float(o[2 * e]) * inv, v1 = __uint_as_float(o[2 * e + 1]) * inv;
+            if (NSPLIT > 1) split_pack2(v0, v1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(v0, v1);
           }
-          tmem_st16(t_s + k * 16, hh);
-          if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + k * 16, ll);
+          const long long off = orow * (AW_HEADS * AW_D) + h * AW_D + ch * 32;
+          uint4* oh = reinterpret_cast<uint4*>(ctx_hi + off);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = make_uint4(hh[4 * e], hh[4 * e + 1], hh[4 * e + 2], hh[4 * e + 3]);
+          if (NSPLIT > 1) {
+            uint4* ol = reinterpret_cast<uint4*>(ctx_lo + off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ol[e] = make_uint4(ll[4 * e], ll[4 * e + 1], ll[4 * e + 2], ll[4 * e + 3]);
+          }
         }
       }
-      tmem_st_wait();
-      if (j == AW_NT - 2) lpart[(it & 1) * 128 + row] = l;      // for the group that finishes the item
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&p_full[grp]);
-        if (j == AW_NT - 2) mbar_arrive(&lpart_full[it & 1]);
-      }
-      if (j == AW_NT - 1) {
-        // ---- this group finishes the item: total row sum, then O / l -> bf16 hi/lo context rows
-        TW_WAIT(4, mbar_wait(&lpart_full[it & 1], uint32_t(it >> 1) & 1u));
-        const float inv = 1.0f / (l + lpart[(it & 1) * 128 + row] * f);   // the other partial is in the scale of m_prev
-        const int item = int(blockIdx.x) + it * int(gridDim.x);
-        const int qt = item % qtiles, bh = item / qtiles;
-        const int h = bh % AW_HEADS, b = bh / AW_HEADS;
-        const int tok = qt * AW_QT + row;
-        const long long orow = (long long)b * AW_TOK + tok;
-        TW_WAIT(5, mbar_wait(&o_full[it & 1], uint32_t(it >> 1) & 1u));
-        tc_fence_after();
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t o[32];
-          tmem_ld32(t_o + ch * 32, o);
-          tmem_ld_wait();
-          if (tok < AW_TOK) {
-            uint32_t hh[16], ll[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float v0 = __uint_as_float(o[2 * e]) * inv, v1 = __uint_as_float(o[2 * e + 1]) * inv;
-              if (NSPLIT > 1) split_pack2(v0, v1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(v0, v1);
-            }
-            const long long off = orow * (AW_HEADS * AW_D) + h * AW_D + ch * 32;
-            uint4* oh = reinterpret_cast<uint4*>(ctx_hi + off);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) oh[e] = make_uint4(hh[4 * e], hh[4 * e + 1], hh[4 * e + 2], hh[4 * e + 3]);
-            if (NSPLIT > 1) {
-              uint4* ol = reinterpret_cast<uint4*>(ctx_lo + off);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ol[e] = make_uint4(ll[4 * e], ll[4 * e + 1], ll[4 * e + 2], ll[4 * e + 3]);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[it & 1]);
-      }
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
     }
-    TW_FLUSH(8, warp == 2 && lane == 0)
+    TW_FLUSH(24, warp == 10 && lane == 0)
   }
 
   tc_fence_before();

@@ -1,5 +1,4 @@
-"""Debug: wait-cycle accounting of the attention kernels' warp roles (library built with -DEB_ATTN_TRACE).
-EGOTAP_ATTN=wide traces attention_wide_kernel instead of attention_kernel."""
+"""Debug: wait-cycle accounting of the attention kernel's warp roles (library built with -DEB_ATTN_TRACE)."""
 import ctypes as C, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,9 +17,8 @@ import torch
 from egotap_b200 import capi
 capi.LIB_PATH = lib
 L = capi.lib()
-wide = os.environ.get("EGOTAP_ATTN") == "wide"
-trace = L.egotap_b200_attn_wide_trace if wide else L.egotap_b200_attn_trace
-Bf = 256
+trace = L.egotap_b200_attn_trace
+Bf = int(os.environ.get("ATTN_TRACE_FRAMES", "256"))
 for prec, name in ((capi.PREC_BF16X3, "x3"), (capi.PREC_BF16, "bf16")):
     x3 = prec == capi.PREC_BF16X3
     qk = torch.randn(Bf * 576, 2048, device="cuda"); vt = torch.randn(Bf * 8 * 128, 576, device="cuda")
@@ -32,14 +30,8 @@ for prec, name in ((capi.PREC_BF16X3, "x3"), (capi.PREC_BF16, "bf16")):
     trace(out, 1)
     v = [x / 148.0 for x in out]
     items = Bf * 8 * 5 / 148.0
-    print("== %s %s (cycles per CTA, %.1f items per CTA)" % ("attention_wide_kernel" if wide else "attention_kernel", name, items))
-    if wide:
-        print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  p_full %.0f  o_empty %.0f | per item %.0f" % (v[0], v[1], v[2], v[4], v[5], v[0] / items))
-        print(" softmax  : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(rescale) %.0f" % (v[8], v[9], v[10], v[11]))
-        print(" producer : total %.0f | wait q_empty %.0f  kv_empty %.0f" % (v[16], v[17], v[18]))
-        print(" epilogue : total %.0f | wait o_full %.0f" % (v[24], v[25]))
-        continue
-    print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  s_empty %.0f  p_full %.0f | per item %.0f" % (v[0], v[1], v[2], v[3], v[4], v[0] / items))
-    print(" softmax  : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(P buf) %.0f  pv_done(last) %.0f  epilogue %.0f" % (v[8], v[9], v[10], v[11], v[12], v[13]))
+    print("== attention_kernel %s (cycles per CTA, %.1f items = %.1f key tiles per CTA)" % (name, items, 5 * items))
+    print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  p_full %.0f  o_empty %.0f | per tile %.0f" % (v[0], v[1], v[2], v[4], v[5], v[0] / items / 5))
+    print(" softmax (warp 2) : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(rescale) %.0f" % (v[8], v[9], v[10], v[11]))
     print(" producer : total %.0f | wait q_empty %.0f  kv_empty %.0f" % (v[16], v[17], v[18]))
-    print(" epilogue : total %.0f | wait o_full %.0f ; MMA wait o_empty %.0f" % (v[24], v[25], v[5]))
+    print(" epilogue : total %.0f | wait o_full %.0f" % (v[24], v[25]))
