@@ -392,13 +392,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
             if (NSPLIT > 1) split_pack2(v0, v1, hh[e], ll[e]); else hh[e] = cvt_bf16x2(v0, v1);
           }
           const long long off = orow * (AW_HEADS * AW_D) + h * AW_D + ch * 32;
-          uint4* oh = reinterpret_cast<uint4*>(ctx_hi + off);
+          // 32-byte stores (row bases are 64-byte aligned: 2048-byte rows, 32-column chunks)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) oh[e] = make_uint4(hh[4 * e], hh[4 * e + 1], hh[4 * e + 2], hh[4 * e + 3]);
+          for (int e = 0; e < 2; ++e)
+            st_global_256(ctx_hi + off + 16 * e, hh[8 * e], hh[8 * e + 1], hh[8 * e + 2], hh[8 * e + 3], hh[8 * e + 4], hh[8 * e + 5],
+                          hh[8 * e + 6], hh[8 * e + 7]);
           if (NSPLIT > 1) {
-            uint4* ol = reinterpret_cast<uint4*>(ctx_lo + off);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ol[e] = make_uint4(ll[4 * e], ll[4 * e + 1], ll[4 * e + 2], ll[4 * e + 3]);
+            for (int e = 0; e < 2; ++e)
+              st_global_256(ctx_lo + off + 16 * e, ll[8 * e], ll[8 * e + 1], ll[8 * e + 2], ll[8 * e + 3], ll[8 * e + 4], ll[8 * e + 5],
+                            ll[8 * e + 6], ll[8 * e + 7]);
           }
         }
       }
@@ -442,6 +445,8 @@ int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const 
   const int qtiles = (query_rows + AW_QT - 1) / AW_QT;
   EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");
   EB_REQUIRE(nsplit == 1 || (qk_lo && vt_lo && ctx_lo), "attention: bf16x3 mode needs the lo parts");
+  EB_REQUIRE(((reinterpret_cast<uintptr_t>(ctx_hi) | reinterpret_cast<uintptr_t>(ctx_lo)) & 31) == 0,
+             "attention: the context buffers must be 32-byte aligned");
   CUtensorMap tm[4];
   int rc;
   const long long fs = (long long)AW_TOK * 2 * AW_HEADS * AW_D;  // frame stride of the qk buffer

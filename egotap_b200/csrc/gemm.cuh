@@ -80,10 +80,23 @@ __device__ __forceinline__ EpiRow epi_row(const EpiParams& p, int g, int m, int 
 }
 // Residual / additive-table chunk of 32 columns; issued BEFORE the accumulator chunk is waited for so the
 // (row-strided, DRAM-latency) loads overlap the TMEM read and the previous chunk's math.
-__device__ __forceinline__ void epi_load_resid(const EpiParams& p, const EpiRow& row, int n0, float4 (&t)[8]) {
-  const float4* r4 = reinterpret_cast<const float4*>(p.resid + row.rrow * p.resid_ld + n0 + p.col_off + row.col_shift);
+__device__ __forceinline__ void epi_load_resid(const EpiParams& p, const EpiRow& row, int n0, float4 (&t)[8], bool wide) {
+  const float* r = p.resid + row.rrow * p.resid_ld + n0 + p.col_off + row.col_shift;
+  if (wide) {            // 32-byte loads: 4 instead of 8 LSU instructions per 32-column chunk of a row
 #pragma unroll
-  for (int j = 0; j < 8; ++j) t[j] = r4[j];
+    for (int j = 0; j < 4; ++j) ld_global_256(r + 8 * j, t[2 * j], t[2 * j + 1]);
+  } else {
+    const float4* r4 = reinterpret_cast<const float4*>(r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = r4[j];
+  }
+}
+// all row starts of the residual / fp32 / bf16 outputs are 32-byte aligned (warp-uniform, evaluated once per kernel)
+__device__ __forceinline__ bool epi_wide_ok(const EpiParams& p) {
+  auto ok = [](const void* ptr, long long ld_bytes) {
+    return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr)) | uintptr_t(ld_bytes)) & 31) == 0;
+  };
+  return ok(p.resid, p.resid_ld * 4) && ok(p.out_f32, p.ldo * 4) && ok(p.out_hi, p.ldo * 2) && ok(p.out_lo, p.ldo * 2);
 }
 
 // Per-column vectors of the epilogue (folded scale, bias) for the 32 columns of a chunk.  They are staged once per tile in
@@ -110,7 +123,7 @@ __device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* 
 }
 
 __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
-                                          const float4 (&t)[8], const float* sv_scale, const float* sv_bias) {
+                                          const float4 (&t)[8], const float* sv_scale, const float* sv_bias, bool wide) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -145,21 +158,43 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row,
     return;
   }
   if (p.out_f32) {
-    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + orow * p.ldo + col);
+    float* o = p.out_f32 + orow * p.ldo + col;
+    if (wide) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 4; ++j)
+        st_global_256(o + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
+                      __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]),
+                      __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+    } else {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
   }
   if (p.out_hi) {
     uint32_t h[16], l[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) split_pack2(v[2 * j], v[2 * j + 1], h[j], l[j]);
-    uint4* oh = reinterpret_cast<uint4*>(p.out_hi + orow * p.ldo + col);
+    __nv_bfloat16* oh = p.out_hi + orow * p.ldo + col;
+    __nv_bfloat16* ol = p.out_lo ? p.out_lo + orow * p.ldo + col : nullptr;
+    if (wide) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-    if (p.out_lo) {
-      uint4* ol = reinterpret_cast<uint4*>(p.out_lo + orow * p.ldo + col);
+      for (int j = 0; j < 2; ++j)
+        st_global_256(oh + 16 * j, h[8 * j], h[8 * j + 1], h[8 * j + 2], h[8 * j + 3], h[8 * j + 4], h[8 * j + 5], h[8 * j + 6], h[8 * j + 7]);
+      if (ol) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ol[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+        for (int j = 0; j < 2; ++j)
+          st_global_256(ol + 16 * j, l[8 * j], l[8 * j + 1], l[8 * j + 2], l[8 * j + 3], l[8 * j + 4], l[8 * j + 5], l[8 * j + 6], l[8 * j + 7]);
+      }
+    } else {
+      uint4* oh4 = reinterpret_cast<uint4*>(oh);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) oh4[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+      if (ol) {
+        uint4* ol4 = reinterpret_cast<uint4*>(ol);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ol4[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+      }
     }
   }
 }
@@ -390,6 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int q = warp & 3;
     const int col_base = ((warp - 2) >> 2) * C::COLS_PER_EPI_GROUP;
     const int et = int(threadIdx.x) - 64;          // epilogue thread = the tile column whose scale / bias it stages
+    const bool wide = epi_wide_ok(ep);             // 32-byte global accesses in the row-domain epilogue
     float* sv_scale = reinterpret_cast<float*>(smem + C::VEC_OFF);
     float* sv_bias = sv_scale + BN;
     int it = 0;
@@ -438,7 +474,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const float* svs = sv_scale + col_base + c * 32;
           const float* svb = sv_bias + col_base + c * 32;
           if (v_part) {
-            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, svs, svb);
+            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, svs, svb, wide);
           } else {
             epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane, svs, svb);
           }
@@ -454,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         continue;
       }
-      if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur);
+      if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur, wide);
 #pragma unroll 1
       for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
         const int n0 = n_first + c * 32;
@@ -462,9 +498,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(t_addr + col_base + c * 32, r);
         const bool more = (c + 1 < C::COLS_PER_EPI_GROUP / 32) && (n0 + 32 < s.N);
-        if (use_resid && more) epi_load_resid(ep, row, n0 + 32, t_nxt);   // prefetch the next chunk's residual
+        if (use_resid && more) epi_load_resid(ep, row, n0 + 32, t_nxt, wide);   // prefetch the next chunk's residual
         tmem_ld_wait();
-        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32);
+        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide);
         if (use_resid && more) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];

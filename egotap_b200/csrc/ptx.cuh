@@ -64,6 +64,19 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256).  A thread that owns one ROW of a tile (tcgen05.ld layout)
+// stores 32 bytes per instruction instead of 16: half as many LSU instructions and full 32-byte sectors per lane.  The address
+// must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, float4& lo, float4& hi) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

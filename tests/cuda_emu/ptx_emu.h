@@ -128,6 +128,17 @@ inline void tmem_dealloc(uint32_t, uint32_t) {}
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 
+inline void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+  if (reinterpret_cast<uintptr_t>(p) % 32) { fprintf(stderr, "ptx_emu: st.global.v8 address not 32-byte aligned\n"); abort(); }
+  const uint32_t v[8] = {a, b, c, d, e, f, g, h};
+  memcpy(p, v, 32);
+}
+inline void ld_global_256(const void* p, float4& lo, float4& hi) {
+  if (reinterpret_cast<uintptr_t>(p) % 32) { fprintf(stderr, "ptx_emu: ld.global.v8 address not 32-byte aligned\n"); abort(); }
+  memcpy(&lo, p, 16);
+  memcpy(&hi, static_cast<const char*>(p) + 16, 16);
+}
+
 constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
