@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libegotap_b200.so")
-SOURCES = ["api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "pu_chain_bwd.cu", "metrics.cu", "plan.cu", "train_ops.cu",
+SOURCES = ["api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "attention_bwd.cu", "pu_chain.cu", "pu_chain_bwd.cu", "metrics.cu", "plan.cu", "train_ops.cu",
            "train_model.cu", "gt_heatmap.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC"]

@@ -30,6 +30,8 @@ EXPORTS = [
     "egotap_b200_bn_bwd", "egotap_b200_regroup_gather", "egotap_b200_pu_cell_fwd", "egotap_b200_pu_cell_bwd",
     "egotap_b200_pu_bridge_gate_bwd", "egotap_b200_pu_chain_bwd", "egotap_b200_head_bwd", "egotap_b200_embed_grads", "egotap_b200_pose_loss",
     "egotap_b200_adamw", "egotap_b200_gt_heatmaps",
+    # fused attention backward (csrc/attention_bwd.cu)
+    "egotap_b200_attention_lse", "egotap_b200_attn_dsum", "egotap_b200_attention_bwd",
 ]
 
 
@@ -75,6 +77,9 @@ def _TRAIN_ARGTYPES(P, LL, I, F):
         "egotap_b200_gelu_bwd": [P, P, LL, P],
         "egotap_b200_layernorm_bwd": [P, P, P, LL, I, I, F, P, I, P, P, P, LL, P],
         "egotap_b200_softmax_bwd": [P, P, LL, I, F, P, P, P, P, P],
+        "egotap_b200_attention_lse": [P, P, P, P, P, P, P, I, I, P],
+        "egotap_b200_attn_dsum": [P, P, P, P, LL, P, P],
+        "egotap_b200_attention_bwd": [P, P, P, P, P, P, I, P],
         "egotap_b200_bn_stats": [P, LL, I, P, P, P, P, P, F, F, P, P, P, P, P, LL, P],
         "egotap_b200_bn_apply": [P, LL, I, P, P, P, P, LL, P, LL, I, I, P],
         "egotap_b200_bn_bwd": [P, P, LL, I, P, P, P, P, P, P, P, LL, P],
@@ -390,6 +395,17 @@ class CudaBackend:
     def attention(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, frames, precision):
         self._c("egotap_b200_attention", _ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
                                            frames, precision, self._st())
+
+    def attention_lse(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, lse, frames, precision):
+        self._c("egotap_b200_attention_lse", _ptr(qk_hi), _ptr(qk_lo), _ptr(vt_hi), _ptr(vt_lo), _ptr(ctx_hi), _ptr(ctx_lo),
+                                               _ptr(lse), frames, precision, self._st())
+
+    def attn_dsum(self, ctx_hi, ctx_lo, dctx_hi, dctx_lo, rows, dsum):
+        self._c("egotap_b200_attn_dsum", _ptr(ctx_hi), _ptr(ctx_lo), _ptr(dctx_hi), _ptr(dctx_lo), rows, _ptr(dsum), self._st())
+
+    def attention_bwd(self, qk_hi, vt_hi, dctx_hi, lse, dsum, dqkv, frames):
+        self._c("egotap_b200_attention_bwd", _ptr(qk_hi), _ptr(vt_hi), _ptr(dctx_hi), _ptr(lse), _ptr(dsum), _ptr(dqkv), frames,
+                                               self._st())
 
     def pu_bridge_gate(self, f, f_ld, f_col, e, e_ld, X, rows, hi, lo):
         self._c("egotap_b200_pu_bridge_gate", _ptr(f), f_ld, f_col, _ptr(e), e_ld, X, rows, _ptr(hi), _ptr(lo), self._st())

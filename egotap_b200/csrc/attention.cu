@@ -64,7 +64,7 @@ struct AttnWideCfg {
   static constexpr int QBUF = NSPLIT == 1 ? 2 : 1;
   static constexpr int BAR_OFF = QBUF * Q_BYTES + NSLOTS * GRAN_BYTES;
   static constexpr int XCHG_OFF = BAR_OFF + 256;             // [2][2][128] row maxima, then [2][2][128] row sums
-  static constexpr int SMEM_BYTES = XCHG_OFF + 4096;         // base must be 1 KB aligned (checked)
+  static constexpr int SMEM_BYTES = XCHG_OFF + 5120;         // base must be 1 KB aligned (checked); + [2][128] final row maxima
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
   static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
@@ -76,7 +76,8 @@ template <int NSPLIT>
 __global__ void __launch_bounds__(AW_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                       const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
-                      __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, int num_items, int qtiles) {
+                      __nv_bfloat16* __restrict__ ctx_hi, __nv_bfloat16* __restrict__ ctx_lo, float* __restrict__ lse,
+                      int num_items, int qtiles) {
   using C = AttnWideCfg<NSPLIT>;
   EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
@@ -95,6 +96,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
   float* xmax = reinterpret_cast<float*>(smem + C::XCHG_OFF);     // [2][2][128]
   float* lsum = xmax + 512;                                        // [2][2][128]
+  float* mfin = lsum + 512;                                        // [2][128] reference maximum at the end of an item (for lse)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_items = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // grid <= num_items
@@ -357,7 +359,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0 + 16, ll);
       }
       tmem_st_wait();
-      if (j == AW_NT - 1) lsum[(it & 1) * 256 + hf * 128 + row] = l;   // for the epilogue warps, ordered by p_full
+      if (j == AW_NT - 1) {                       // for the epilogue warps, ordered by p_full
+        lsum[(it & 1) * 256 + hf * 128 + row] = l;
+        if (hf == 0) mfin[(it & 1) * 128 + row] = m_ref;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
@@ -376,9 +381,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       const int ob = it & 1;
       TW_WAIT(1, mbar_wait(&o_full[ob], (it >> 1) & 1));
       tc_fence_after();
-      const float inv = 1.0f / (lsum[ob * 256 + row] + lsum[ob * 256 + 128 + row]);
+      const float l_tot = lsum[ob * 256 + row] + lsum[ob * 256 + 128 + row];
+      const float inv = 1.0f / l_tot;
       const int tok = qt * AW_QT + row;
       const long long orow = (long long)b * AW_TOK + tok;
+      // training: log-sum-exp of the row in the exp2 domain, P = exp2(s * c - lse), for the fused backward (attention_bwd.cu)
+      if (lse != nullptr && tok < AW_TOK)
+        lse[(long long)bh * AW_TOK + tok] = mfin[ob * 128 + row] * (0.08838834764831845f * 1.4426950408889634f) + log2f(l_tot);
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t o[32];
@@ -418,8 +427,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
 }
 
 template <int NSPLIT>
-static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int qtiles,
-                                 cudaStream_t stream) {
+static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, float* lse, int B, int qtiles,
+                            cudaStream_t stream) {
   using C = AttnWideCfg<NSPLIT>;
   auto kern = attention_kernel<NSPLIT>;
   static bool attr_done[64] = {false};
@@ -431,7 +440,7 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
   const int items = B * AW_HEADS * qtiles;
   const int grid = items < num_sms() ? items : num_sms();
   ProfScope prof("attention_kernel", stream);
-  EB_LAUNCH_SMEM(kern, grid, AW_THREADS, C::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3], ctx_hi, ctx_lo, items, qtiles);
+  EB_LAUNCH_SMEM(kern, grid, AW_THREADS, C::SMEM_BYTES, stream, tm[0], tm[1], tm[2], tm[3], ctx_hi, ctx_lo, lse, items, qtiles);
   EB_CHECK_LAUNCH("attention_kernel");
   return 0;
 }
@@ -439,8 +448,8 @@ static int launch_attention(const CUtensorMap* tm, __nv_bfloat16* ctx_hi, __nv_b
 // qk: (B*576, 2048) = [Q | K] per token, head h at columns h*128; vt: (B*8*128, 576) = V^T per (frame, head)
 // query_rows: only the first query_rows tokens of every frame get a context row (all 576 are keys / values)
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
-                       const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
-                       int query_rows, cudaStream_t stream) {
+                  const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
+                  int query_rows, cudaStream_t stream, float* lse) {
   EB_REQUIRE(query_rows > 0 && query_rows <= AW_TOK, "attention: query_rows must be in (0, 576]");
   const int qtiles = (query_rows + AW_QT - 1) / AW_QT;
   EB_REQUIRE(qk_hi && vt_hi && ctx_hi && B > 0, "attention: bad arguments");
@@ -460,8 +469,8 @@ int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const 
       return rc;
   }
   if (nsplit == 1) { tm[1] = tm[0]; tm[3] = tm[2]; }
-  return nsplit == 3 ? launch_attention<3>(tm, ctx_hi, ctx_lo, B, qtiles, stream)
-                     : launch_attention<1>(tm, ctx_hi, ctx_lo, B, qtiles, stream);
+  return nsplit == 3 ? launch_attention<3>(tm, ctx_hi, ctx_lo, lse, B, qtiles, stream)
+                     : launch_attention<1>(tm, ctx_hi, ctx_lo, lse, B, qtiles, stream);
 }
 
 }  // namespace eb
@@ -479,4 +488,12 @@ extern "C" int egotap_b200_attention(const void* qk_hi, const void* qk_lo, const
   return eb::attention_run((const __nv_bfloat16*)qk_hi, (const __nv_bfloat16*)qk_lo, (const __nv_bfloat16*)vt_hi,
                            (const __nv_bfloat16*)vt_lo, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo, frames,
                            precision == EGOTAP_PREC_BF16 ? 1 : 3, eb::AW_TOK, (cudaStream_t)stream);
+}
+
+/* the same with the per-row log-sum-exp (exp2 domain) written to lse[(frame * 8 + head) * 576 + token]: training forward */
+extern "C" int egotap_b200_attention_lse(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo,
+                                         void* ctx_hi, void* ctx_lo, float* lse, int frames, int precision, void* stream) {
+  return eb::attention_run((const __nv_bfloat16*)qk_hi, (const __nv_bfloat16*)qk_lo, (const __nv_bfloat16*)vt_hi,
+                           (const __nv_bfloat16*)vt_lo, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo, frames,
+                           precision == EGOTAP_PREC_BF16 ? 1 : 3, eb::AW_TOK, (cudaStream_t)stream, lse);
 }

@@ -23,7 +23,12 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
 // attention.cu
 int attention_run(const __nv_bfloat16* qk_hi, const __nv_bfloat16* qk_lo, const __nv_bfloat16* vt_hi,
                   const __nv_bfloat16* vt_lo, __nv_bfloat16* ctx_hi, __nv_bfloat16* ctx_lo, int B, int nsplit,
-                  int query_rows, cudaStream_t stream);
+                  int query_rows, cudaStream_t stream, float* lse = nullptr);
+// attention_bwd.cu (bf16-operand training mode)
+int attention_bwd_run(const __nv_bfloat16* qk, const __nv_bfloat16* vt, const __nv_bfloat16* dctx, const float* lse,
+                      const float* dsum, float* dqkv, int B, cudaStream_t stream);
+int attn_dsum_run(const __nv_bfloat16* o_hi, const __nv_bfloat16* o_lo, const __nv_bfloat16* do_hi, const __nv_bfloat16* do_lo,
+                  long long rows, float* dsum, cudaStream_t stream);
 
 // pu_chain.cu
 int pu_permute_split_run(const float* W, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t stream);

@@ -22,6 +22,7 @@ Dataflow conventions
     training all-reduces contiguous slices while earlier layers are still being differentiated
 """
 import math
+import os
 
 import torch
 
@@ -160,6 +161,10 @@ class TrainEngine:
         # Opt-in: BPTT of each propagation layer as ONE persistent launch (csrc/pu_chain_bwd.cu) instead of J x
         # (cell-backward kernel + dgates . W_hh GEMM); same arithmetic
         self.persistent_bptt = False
+        # bf16-operand mode: attention backward as two fused tcgen05 kernels that keep scores / probabilities on chip
+        # (csrc/attention_bwd.cu); the fp32-parity mode (gradient checks) keeps the GEMM-based path below.  Set before the
+        # first step; False selects the GEMM-based path in bf16 mode too (A/B).
+        self.fused_attention_bwd = (not self.x3) and hasattr(self.be, "attention_bwd") and os.environ.get("EGOTAP_ATTN_BWD") != "gemm"
         self._graph, self._graph_key, self._graph_warm = None, None, None
         self._alloc_weights()
         self.scr = self.be.empty((4 * 1024 * 1024,), torch.float32)     # reduction scratch shared by the small ops
@@ -293,7 +298,7 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------------ activations
     def _alloc(self, B):
-        if self.batch == B:
+        if self.batch == B and getattr(self, "_alloc_fused", None) == bool(self.fused_attention_bwd):
             return
         J, n_hm, live = self.J, self.n_hm, self.live
         M, R, RJ = B * TOK, B * n_hm, B * J
@@ -306,6 +311,9 @@ class TrainEngine:
             A[n] = [pair(M, c) for _ in range(3)]
         A["vt"] = [pair(B * HEADS * HD, TOK) for _ in range(3)]        # V^T per (frame, head), as STORE_QKV writes it
         A["u"] = [f32(M, MLPD) for _ in range(3)]
+        fused = self._alloc_fused = bool(self.fused_attention_bwd)
+        if fused:
+            A["lse"] = [f32(B * HEADS * TOK) for _ in range(3)]     # per-row log-sum-exp of the forward (exp2 domain)
         A["fin"] = pair(R, 16 * HID)
         for e in ("p", "r"):
             for i, n in enumerate((2048, 512, EMB)):
@@ -327,14 +335,17 @@ class TrainEngine:
         t_elems = max(MLPD * ldM, 16 * HID * ldR, 5 * PUH * ldJ)
         S["TA"], S["TB"] = pair(1, t_elems), pair(1, t_elems)   # transposed gradient / transposed activation
         S["dctx"] = pair(M, HID)
-        Bc = min(B, self.attn_chunk)
-        Gc = Bc * HEADS
-        S["Sc"], S["dP"] = f32(Gc * TOK, TOK), f32(Gc * TOK, TOK)
-        for n in ("P", "dS", "PT", "dST"):
-            S[n] = pair(Gc * TOK, TOK)
-        for n in ("QT", "KT", "dctxT"):
-            S[n] = pair(Gc * HD, TOK)
-        S["V"] = pair(Gc * TOK, HD)
+        if fused:
+            S["dsum"] = f32(B * HEADS * TOK)
+        else:       # score / probability scratch of the GEMM-based attention backward, per chunk of frames
+            Bc = min(B, self.attn_chunk)
+            Gc = Bc * HEADS
+            S["Sc"], S["dP"] = f32(Gc * TOK, TOK), f32(Gc * TOK, TOK)
+            for n in ("P", "dS", "PT", "dST"):
+                S[n] = pair(Gc * TOK, TOK)
+            for n in ("QT", "KT", "dctxT"):
+                S[n] = pair(Gc * HD, TOK)
+            S["V"] = pair(Gc * TOK, HD)
         S["da"] = f32(R, 16 * HID)                            # FC-encoder gradient ping
         S["db"] = f32(R, 2048)                                # ... and pong
         S["dE"], S["dSkel"], S["dH0"] = f32(RJ, 2 * PUX), f32(RJ, PUH), f32(RJ, PUH)
@@ -380,7 +391,10 @@ class TrainEngine:
                          ln1.hi, ln1.lo, None)
             self._gemm(ln1, HID, M, HID, W["qkv%d" % l], HID, 3 * HID, bias=self.b_qkv[l], store=STORE_QKV,
                        qk_cols=2 * HID, tokens=TOK, out=qk, ldo=2 * HID, vt_hi=vt.hi, vt_lo=vt.lo)
-            be.attention(qk.hi, qk.lo, vt.hi, vt.lo, ctx.hi, ctx.lo, B, self.precision)
+            if self._alloc_fused:
+                be.attention_lse(qk.hi, qk.lo, vt.hi, vt.lo, ctx.hi, ctx.lo, A["lse"][l], B, self.precision)
+            else:
+                be.attention(qk.hi, qk.lo, vt.hi, vt.lo, ctx.hi, ctx.lo, B, self.precision)
             self._gemm(ctx, HID, M, HID, W["o%d" % l], HID, HID, bias=P[p + "attention.output.dense.bias"],
                        resid=h_in, resid_ld=HID, out_f32=h_mid, ldo=HID)
             be.layernorm(h_mid, P[p + "layernorm_after.weight"], P[p + "layernorm_after.bias"], B, TOK, TOK, LN_EPS,
@@ -566,7 +580,11 @@ class TrainEngine:
             self._dw(TA, TB, HID, HID, M, ldM, g[p + "attention.output.dense.weight"])
             dctx = S["dctx"]
             self._gemm(rm, HID, M, HID, WT["o%d" % l], HID, HID, out=dctx, ldo=HID)
-            self._attention_bwd(B, qk, vt, dctx, dA)         # dA <- d[Q | K | V]  (M x 3072)
+            if self._alloc_fused:                            # dA <- d[Q | K | V]  (M x 3072)
+                be.attn_dsum(ctx.hi, ctx.lo, dctx.hi, dctx.lo, M, S["dsum"])
+                be.attention_bwd(qk.hi, vt.hi, dctx.hi, A["lse"][l], S["dsum"], dA, B)
+            else:
+                self._attention_bwd(B, qk, vt, dctx, dA)
             self._tsplit(dA, M, 3 * HID, 3 * HID, rm, TA, ldM, bias=S["dpos"])     # (3072,) sums into a spare buffer
             for q, n in enumerate(("query", "key", "value")):
                 be.copy(g[p + "attention.attention.%s.bias" % n], S["dpos"].view(-1)[q * HID:(q + 1) * HID])

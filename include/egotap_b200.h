@@ -218,6 +218,17 @@ int egotap_b200_layernorm_bwd(const float* dy, const float* x, const float* w, l
 /* P = softmax(S) ; dS = P * (dP - rowsum(P * dP)) * scale ; S, dP fp32 (rows x 576) */
 int egotap_b200_softmax_bwd(const float* S, const float* dP, long long rows, int cols, float scale, void* p_hi, void* p_lo,
                             void* ds_hi, void* ds_lo, void* stream);
+/* Fused attention backward of the bf16-operand training mode (csrc/attention_bwd.cu; autograd of reference
+ * model/modeling_vit.py:233-252).  attention_lse = egotap_b200_attention that also writes the per-row log-sum-exp in the exp2
+ * domain, lse[(frame*8 + head)*576 + token] = max * c + log2(sum), c = log2(e)/sqrt(128).  attn_dsum: D = rowsum(dctx o ctx)
+ * per (frame, head, token), same indexing (rows = frames*576).  attention_bwd: dqkv (frames*576, 3072) fp32 =
+ * [dQ | dK | dV], head h at columns h*128 of each 1024-column third; scores and probabilities never leave the SM. */
+int egotap_b200_attention_lse(const void* qk_hi, const void* qk_lo, const void* vt_hi, const void* vt_lo, void* ctx_hi,
+                              void* ctx_lo, float* lse, int frames, int precision, void* stream);
+int egotap_b200_attn_dsum(const void* ctx_hi, const void* ctx_lo, const void* dctx_hi, const void* dctx_lo, long long rows,
+                          float* dsum, void* stream);
+int egotap_b200_attention_bwd(const void* qk_hi, const void* vt_hi, const void* dctx_hi, const float* lse, const float* dsum,
+                              float* dqkv, int frames, void* stream);
 /* train-mode BatchNorm1d: batch statistics + running-buffer update + folded scale/shift; apply with LeakyReLU(0.2)
  * (optionally into the per-joint [left | right] layout); backward through LeakyReLU and the batch statistics */
 int egotap_b200_bn_stats(const float* y, long long rows, int cols, const float* gamma, const float* beta, float* running_mean,

@@ -305,6 +305,46 @@ class OracleBackend:
         self.launches += 1
         flat(out)[:n] = flat(partials)[:G * n].view(G, n).sum(0)
 
+    def attention_lse(self, qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, lse, frames, precision):
+        """attention() + the per-row log-sum-exp in the exp2 domain: lse[(frame, head, token)] = log2(sum_k exp(s_k))"""
+        self.attention(qk_hi, qk_lo, vt_hi, vt_lo, ctx_hi, ctx_lo, frames, precision)
+        if precision != PREC_BF16X3:
+            qk_lo = None
+        qk = pair_f32(qk_hi, qk_lo, (frames, 576, 2048), (576 * 2048, 2048, 1)).double()
+        q = qk[..., :1024].view(frames, 576, 8, 128).permute(0, 2, 1, 3)
+        k = qk[..., 1024:].view(frames, 576, 8, 128).permute(0, 2, 1, 3)
+        s = q @ k.transpose(-1, -2) / math.sqrt(128.0)
+        flat(lse)[:frames * 8 * 576] = (torch.logsumexp(s, -1) / math.log(2.0)).float().reshape(-1)
+
+    def attn_dsum(self, ctx_hi, ctx_lo, dctx_hi, dctx_lo, rows, dsum):
+        """D[(frame, head, token)] = sum_d dctx * ctx over the head's 128 columns"""
+        self.launches += 1
+        frames = rows // 576
+        o = pair_f32(ctx_hi, ctx_lo, (frames, 576, 8, 128), (576 * 1024, 1024, 128, 1)).double()
+        g = pair_f32(dctx_hi, dctx_lo, (frames, 576, 8, 128), (576 * 1024, 1024, 128, 1)).double()
+        flat(dsum)[:frames * 8 * 576] = (o * g).sum(-1).permute(0, 2, 1).float().reshape(-1)
+
+    def attention_bwd(self, qk_hi, vt_hi, dctx_hi, lse, dsum, dqkv, frames):
+        """fused backward, bf16 operands: P = exp2(s*c - lse), dS = P (dP - D) / sqrt(128); dqkv (frames*576, 3072) fp32 =
+        [dQ | dK | dV].  P and dS are bf16 MMA operands in the kernel (rounded here unless ``exact``)."""
+        self.launches += 1
+        qk = pair_f32(qk_hi, None, (frames, 576, 2048), (576 * 2048, 2048, 1)).double()
+        vt = pair_f32(vt_hi, None, (frames, 8, 128, 576), (8 * 128 * 576, 128 * 576, 576, 1)).double()
+        do = pair_f32(dctx_hi, None, (frames, 576, 8, 128), (576 * 1024, 1024, 128, 1)).double().permute(0, 2, 1, 3)
+        q = qk[..., :1024].view(frames, 576, 8, 128).permute(0, 2, 1, 3)
+        k = qk[..., 1024:].view(frames, 576, 8, 128).permute(0, 2, 1, 3)
+        v = vt.transpose(-1, -2)
+        L = flat(lse)[:frames * 8 * 576].view(frames, 8, 576, 1).double()
+        D = flat(dsum)[:frames * 8 * 576].view(frames, 8, 576, 1).double()
+        scale = 1.0 / math.sqrt(128.0)
+        p = torch.exp2(q @ k.transpose(-1, -2) * (scale / math.log(2.0)) - L)
+        ds = p * ((do @ v.transpose(-1, -2)) - D) * scale
+        if not self.exact:
+            p, ds = p.to(torch.bfloat16).double(), ds.to(torch.bfloat16).double()
+        dq, dk, dv = ds @ k, ds.transpose(-1, -2) @ q, p.transpose(-1, -2) @ do
+        out = torch.cat([t.permute(0, 2, 1, 3).reshape(frames * 576, 1024) for t in (dq, dk, dv)], 1).float()
+        flat(dqkv)[:out.numel()] = out.reshape(-1)
+
     def gelu_fwd(self, u, n, out_hi, out_lo):
         """reference ACT2FN['gelu'] (exact erf), model/modeling_vit.py:326"""
         self.launches += 1

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "egotap_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libtrain_emu.so")
 SOURCES = [os.path.join(HERE, "cuda_emu.cpp"), os.path.join(HERE, "selftest.cu"), os.path.join(CSRC, "kernels.cu"), os.path.join(CSRC, "gemm_launch.cu"),
-           os.path.join(CSRC, "attention.cu"), os.path.join(CSRC, "pu_chain.cu"), os.path.join(CSRC, "pu_chain_bwd.cu"), os.path.join(CSRC, "metrics.cu"),
+           os.path.join(CSRC, "attention.cu"), os.path.join(CSRC, "attention_bwd.cu"), os.path.join(CSRC, "pu_chain.cu"), os.path.join(CSRC, "pu_chain_bwd.cu"), os.path.join(CSRC, "metrics.cu"),
            os.path.join(CSRC, "plan.cu"),
            os.path.join(CSRC, "train_ops.cu"),
            os.path.join(CSRC, "train_model.cu"),
@@ -105,6 +105,18 @@ def make_backend(real_tensor_core=False, all_oracle=False, dry=False):
             else:
                 self._py(orc.attention, *a)
 
+        def attention_lse(self, *a):
+            if real_tensor_core:
+                capi.CudaBackend.attention_lse(self, *a)
+            else:
+                self._py(orc.attention_lse, *a)
+
+        def attention_bwd(self, *a):
+            if real_tensor_core:
+                capi.CudaBackend.attention_bwd(self, *a)
+            else:
+                self._py(orc.attention_bwd, *a)
+
         # ... but their SOURCE does run on the functional tcgen05 / TMA / mbarrier model (ptx_emu.h), for op-level tests
         def gemm_tc(self, *a, **k):
             saved, capi.require_cuda = capi.require_cuda, (lambda *t: None)
@@ -136,7 +148,9 @@ def make_backend(real_tensor_core=False, all_oracle=False, dry=False):
         EmuBackend = type("DryBackend", (EmuBackend,), dict(
             empty=lambda self, shape, dtype=None: torch.empty(shape, dtype=dtype or torch.float32),
             zero=lambda self, t: None, copy=lambda self, d, s_: None,
-            gemm=lambda self, *a, **k: self.gemm_tc(*a, **k), attention=lambda self, *a: self.attention_tc(*a)))
+            gemm=lambda self, *a, **k: self.gemm_tc(*a, **k), attention=lambda self, *a: self.attention_tc(*a),
+            attention_lse=lambda self, *a: capi.CudaBackend.attention_lse(self, *a),
+            attention_bwd=lambda self, *a: capi.CudaBackend.attention_bwd(self, *a)))
     return EmuBackend(), orc
 
 

@@ -177,6 +177,22 @@ inline void emu_load_smem_operand(const uint8_t* smem, uint64_t desc, int rows, 
       for (int k = 0; k < 8; ++k) out[r * 16 + ch * 8 + k] = __uint_as_float(uint32_t(v[k]) << 16);
     }
 }
+// operand tile (rows x 16) of an MN-major, 128B-swizzled descriptor: canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in
+// bf16 elements (CUTLASS cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): the M/N index runs along the 128-byte row
+// (64 elements), the next 64 M/N elements are LBO bytes further; the K index selects the row: 8 rows per 1 KB swizzle atom, the
+// next 8 rows SBO bytes further.  out[r * 16 + k] like the K-major loader.
+inline void emu_load_smem_operand_mn(const uint8_t* smem, uint64_t desc, int rows, float* out) {
+  if (((desc >> 61) & 7) != 2 || ((desc >> 46) & 3) != 1) { fprintf(stderr, "ptx_emu: unsupported matrix descriptor\n"); abort(); }
+  const uint32_t start = uint32_t(desc & 0x3FFF) << 4, lbo = uint32_t((desc >> 16) & 0x3FFF) << 4, sbo = uint32_t((desc >> 32) & 0x3FFF) << 4;
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < 16; ++k) {
+      uint32_t addr = start + uint32_t(r / 64) * lbo + uint32_t(k / 8) * sbo + uint32_t(k % 8) * 128 + uint32_t(r % 64) * 2;
+      out[r * 16 + k] = emu_bf16_at(smem, addr);
+    }
+}
+inline void emu_load_operand(const uint8_t* smem, uint64_t desc, int rows, bool mn_major, float* out) {
+  if (mn_major) emu_load_smem_operand_mn(smem, desc, rows, out); else emu_load_smem_operand(smem, desc, rows, out);
+}
 __attribute__((no_sanitize("alignment"))) inline void emu_mma_accumulate(uint32_t* tmem, uint32_t lane0, uint32_t col, int M,
                                                                          int N, const float* A, const float* B, bool acc) {
   static float Bt[16 * 256];                              // B transposed to [k][n]: the n loop then vectorises
@@ -199,13 +215,14 @@ template <int CG>
 inline void umma_bf16_now(int rank, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   const int M = int((idesc >> 24) & 31) << 4, N = int((idesc >> 17) & 63) << 3;
   const uint32_t col = tmem_d & 0xFFFF, lane0 = tmem_d >> 16;
-  if (((idesc >> 15) & 3) != 0 || col + N > 512 || lane0 != 0) { fprintf(stderr, "ptx_emu: unsupported MMA (idesc %x tmem %x)\n", idesc, tmem_d); abort(); }
+  const bool a_mn = ((idesc >> 15) & 1) != 0, b_mn = ((idesc >> 16) & 1) != 0;
+  if (col + N > 512 || lane0 != 0 || (CG != 1 && (a_mn || b_mn))) { fprintf(stderr, "ptx_emu: unsupported MMA (idesc %x tmem %x)\n", idesc, tmem_d); abort(); }
   static float A[256 * 16], B[256 * 16];
   if (CG == 1) {
     if (M != 128) { fprintf(stderr, "ptx_emu: cta_group::1 MMA with M = %d\n", M); abort(); }
     const uint8_t* smem = eb_emu::smem_of(rank);
-    emu_load_smem_operand(smem, adesc, M, A);
-    emu_load_smem_operand(smem, bdesc, N, B);
+    emu_load_operand(smem, adesc, M, a_mn, A);
+    emu_load_operand(smem, bdesc, N, b_mn, B);
     emu_mma_accumulate(eb_emu::tmem_of(rank), 0, col, M, N, A, B, accumulate != 0);
   } else {
     if (M != 256 || rank != 0) { fprintf(stderr, "ptx_emu: cta_group::2 MMA must be issued by the leader with M = 256\n"); abort(); }
@@ -266,7 +283,7 @@ inline void umma_bf16_ts_now(int rank, uint32_t tmem_d, uint32_t tmem_a, uint64_
       A[m * 16 + 2 * c] = __uint_as_float(w << 16);
       A[m * 16 + 2 * c + 1] = __uint_as_float(w & 0xffff0000u);
     }
-  emu_load_smem_operand(eb_emu::smem_of(rank), bdesc, N, B);
+  emu_load_operand(eb_emu::smem_of(rank), bdesc, N, ((idesc >> 16) & 1) != 0, B);
   emu_mma_accumulate(t, 0, col, M, N, A, B, accumulate != 0);
 }
 inline void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

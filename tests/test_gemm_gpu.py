@@ -154,6 +154,49 @@ def test_fused_attention_matches_torch(x3, case):
     assert rel < tol, (case, x3, rel)
 
 
+@pytest.mark.parametrize("case", ["normal", "wide_scores", "one_frame"])
+def test_fused_attention_backward_matches_autograd(case):
+    """csrc/attention_bwd.cu (bf16-operand training mode): the forward's log-sum-exp output, attn_dsum and the two fused backward
+    kernels (K-major and MN-major shared-memory operands of the same TMA tiles, P^T / dS^T written in place in tensor memory)
+    against torch.autograd in fp64 on the same bf16-rounded Q, K, V, dO.  P and dS are bf16 MMA operands in the kernels, so the
+    gradients carry a ~2^-9 relative rounding per term: direction and norm are asserted tightly, elements loosely."""
+    from egotap_b200 import capi
+    torch.manual_seed(11)
+    Bf, T, H, Dh = (1 if case == "one_frame" else 3), 576, 8, 128
+    q = torch.randn(Bf, H, T, Dh, device="cuda") * (2.5 if case == "wide_scores" else 1.0)
+    k = torch.randn(Bf, H, T, Dh, device="cuda")
+    v = torch.randn(Bf, H, T, Dh, device="cuda")
+    do = torch.randn(Bf, H, T, Dh, device="cuda")
+    qk = torch.cat([q.permute(0, 2, 1, 3).reshape(Bf * T, H * Dh), k.permute(0, 2, 1, 3).reshape(Bf * T, H * Dh)], 1).contiguous()
+    vt = v.transpose(-1, -2).reshape(Bf * H * Dh, T).contiguous()
+    qk_h, vt_h = qk.to(torch.bfloat16), vt.to(torch.bfloat16)
+    dctx_h = do.permute(0, 2, 1, 3).reshape(Bf * T, H * Dh).contiguous().to(torch.bfloat16)
+    be = capi.CudaBackend()
+    ctx_h = torch.empty(Bf * T, H * Dh, device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((Bf * H * T,), float("nan"), device="cuda")
+    dsum = torch.full((Bf * H * T,), float("nan"), device="cuda")
+    dqkv = torch.full((Bf * T, 3 * H * Dh), float("nan"), device="cuda")
+    be.attention_lse(qk_h, None, vt_h, None, ctx_h, None, lse, Bf, capi.PREC_BF16)
+    be.attn_dsum(ctx_h, None, dctx_h, None, Bf * T, dsum)
+    be.attention_bwd(qk_h, vt_h, dctx_h, lse, dsum, dqkv, Bf)
+    torch.cuda.synchronize()
+    assert not torch.isnan(dqkv).any() and not torch.isnan(lse).any()
+    qr = qk_h[:, :H * Dh].double().view(Bf, T, H, Dh).permute(0, 2, 1, 3).requires_grad_(True)
+    kr = qk_h[:, H * Dh:].double().view(Bf, T, H, Dh).permute(0, 2, 1, 3).requires_grad_(True)
+    vr = vt_h.double().view(Bf, H, Dh, T).transpose(-1, -2).requires_grad_(True)
+    dor = dctx_h.double().view(Bf, T, H, Dh).permute(0, 2, 1, 3)
+    s = qr @ kr.transpose(-1, -2) / Dh ** 0.5
+    out = torch.softmax(s, -1) @ vr
+    out.backward(dor)
+    ref_lse = torch.logsumexp(s.detach(), -1) / 0.6931471805599453
+    assert (lse.double().view(Bf, H, T) - ref_lse).abs().max().item() < 5e-3
+    for name, i, ref in (("dQ", 0, qr.grad), ("dK", 1, kr.grad), ("dV", 2, vr.grad)):
+        got = dqkv[:, i * H * Dh:(i + 1) * H * Dh].double().view(Bf, T, H, Dh).permute(0, 2, 1, 3)
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()))
+        assert cos > 0.9995 and abs(float(got.norm() / ref.norm()) - 1) < 5e-3, (name, cos, float(got.norm() / ref.norm()))
+        assert ((got - ref).abs().max() / ref.abs().max()).item() < 4e-2, name
+
+
 def test_argument_errors_are_reported_not_fatal():
     from egotap_b200 import capi
     A = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)

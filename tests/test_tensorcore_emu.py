@@ -17,7 +17,7 @@ import torch
 import op_oracle
 import train_oracle as tro
 import weights
-from egotap_b200 import training
+from egotap_b200 import capi, training
 from egotap_b200.synthetic import synthetic_heatmaps
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cuda_emu"))
@@ -242,6 +242,49 @@ def test_fused_attention_kernel(be, prec, variant):
     emu, orc = be
     with _env("EGOTAP_ATTN", variant):
         _fused_attention_case(emu, orc, prec)
+
+
+def test_fused_attention_backward_kernels(be):
+    """csrc/attention_bwd.cu on the functional model: the forward kernel's log-sum-exp output, attn_dsum, and the two backward
+    kernels (K-major AND MN-major shared-memory operands, TS-form MMAs with P^T / dS^T written in place over S^T / dP^T) against
+    the op oracle, i.e. against autograd's formulas in fp64 with the kernel's bf16 roundings of P and dS.  2 frames = 80 work
+    items per kernel on the emulated device (several items per persistent CTA: every barrier's phase parity wraps); frame 0
+    has a large score spread."""
+    emu, orc = be
+    torch.manual_seed(41)
+    frames = 2
+    qk = torch.randn(frames * 576, 2048) * 1.2
+    qk[:576, :1024] *= 3.0
+    vt = torch.randn(frames * 8 * 128, 576)
+    dctx = torch.randn(frames * 576, 1024)
+    qh, vh, dh = qk.to(BF16), vt.to(BF16), dctx.to(BF16)
+    n_stat = frames * 8 * 576
+    res = []
+    for b_ in (emu, orc):
+        ctx = torch.full((frames * 576, 1024), float("nan"), dtype=BF16)
+        lse = torch.full((n_stat,), float("nan"))
+        if b_ is emu:
+            capi.CudaBackend.attention_lse(emu, qh, None, vh, None, ctx, None, lse, frames, 1)
+        else:
+            b_.attention_lse(qh, None, vh, None, ctx, None, lse, frames, 1)
+        dsum = torch.full((n_stat,), float("nan"))
+        b_.attn_dsum(ctx, None, dh, None, frames * 576, dsum)
+        dqkv = torch.full((frames * 576, 3072), float("nan"))
+        if b_ is emu:
+            capi.CudaBackend.attention_bwd(emu, qh, vh, dh, lse, dsum, dqkv, frames)
+        else:
+            b_.attention_bwd(qh, vh, dh, lse, dsum, dqkv, frames)
+        res.append((ctx.float(), lse, dsum, dqkv))
+    (c1, l1, d1, g1), (c2, l2, d2, g2) = res
+    assert not torch.isnan(g1).any() and not torch.isnan(l1).any()
+    _close(c1, c2, 1.5e-2)
+    assert (l1 - l2).abs().max().item() < 2e-3          # exp2-domain log-sum-exp (values of order 10)
+    _close(d1, d2, 2e-2)                               # D sums the two implementations' bf16-rounded context rows
+    for name, sl in (("dQ", slice(0, 1024)), ("dK", slice(1024, 2048)), ("dV", slice(2048, 3072))):
+        a, b = g1[:, sl].double(), g2[:, sl].double()
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > 0.9995 and abs(float(a.norm() / b.norm()) - 1) < 5e-3, (name, cos, float(a.norm() / b.norm()))
+        assert (a - b).abs().max().item() <= 4e-2 * b.abs().max().item(), name
 
 
 def _fused_attention_case(emu, orc, prec):
@@ -482,7 +525,7 @@ _DRY_CODE = r'''
 import ctypes as C, json, os, sys
 sys.path[:0] = %r
 import torch, build_emu, weights
-from egotap_b200 import training
+from egotap_b200 import capi, training
 kind, preset, B, prec, extra = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5]
 lib = C.CDLL(build_emu.build()); lib.egotap_b200_last_error.restype = C.c_char_p; lib.egotap_b200_param_name.restype = C.c_char_p
 lib.emu_set_dry_run.restype = C.c_longlong
