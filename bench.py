@@ -270,6 +270,8 @@ def measure_lifting(ctx, args, preset, B, precision, workload="lifting", graph=F
 
     for _ in range(W):
         pose = local_step()
+    if world > 1:                 # the communicator's first all-gather sets up its channels (~100 ms): not part of the job
+        gather_job_poses(torch.stack([pose, pose]))
     torch.cuda.synchronize()
     # ---------------- parity of what is being timed (PARITY_FRAMES frames through the oracle, rank 0)
     parity = None
@@ -559,6 +561,8 @@ def run_train(args):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if red is not None:
+        red.time_exposed = True
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for _ in range(K):
@@ -566,6 +570,12 @@ def run_train(args):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    comm = None
+    if red is not None:
+        comm = dict(exposed_ms_per_step=red.exposed_ms(), bytes_per_step=int(eng.flat_grad.numel()) * 4, collectives_per_step=len(red.launched),
+                    note="gradient all-reduce (NCCL, SUM) launched per >= 32 MB slice of the flat gradient buffer as soon as the backward "
+                         "has finished it; exposed = CUDA-event time the compute stream waits for the collectives before AdamW (rank 0)")
+        red.time_exposed = False
     launches = capi.lib().egotap_b200_launch_count() - launches0
     losses.append(loss.clone())
     # end to end: inputs and targets from pinned host memory every step, the loss read back every step
@@ -573,11 +583,32 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    # the next batch is uploaded on a copy stream into one of two staging buffers while the current step runs (the engine
+    # copies its inputs into its own buffers at the start of a step, so a staging buffer is free again after that step)
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [(torch.empty_like(x), torch.empty_like(gt)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    compute = torch.cuda.current_stream(dev)
+
+    def upload(i):
+        s_ = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[s_])
+            stage[s_][0].copy_(x_host, non_blocking=True)
+            stage[s_][1].copy_(gt_host, non_blocking=True)
+            ready[s_].record(copy_stream)
+    for ev in done:
+        ev.record(compute)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(K):
-        xd, gd = x_host.to(dev, non_blocking=True), gt_host.to(dev, non_blocking=True)
-        loss_host.copy_(eng.train_step(xd, gd, reducer=red), non_blocking=True)
+    upload(0)
+    for i in range(K):
+        if i + 1 < K:
+            upload(i + 1)
+        compute.wait_event(ready[i % 2])
+        loss_host.copy_(eng.train_step(stage[i % 2][0], stage[i % 2][1], reducer=red), non_blocking=True)
+        done[i % 2].record(compute)
     t1.record()
     torch.cuda.synchronize()
     ms_e2e = t0.elapsed_time(t1)
@@ -617,6 +648,7 @@ def run_train(args):
                               traffic=None, mma_passes_per_flop=nsplit, gemm_share_of_step=gemm_ms / (ms / K),
                               peak_source=pk["source"] + ", sustained bf16 figure"),
                 kernel_ms_per_step={k: round(v, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1])},
+                allreduce=comm,
                 loss_trace=[float(l[0]) for l in losses],
                 cpu_baseline=(dict(value=cpu["fps"], unit="frames/s", cores=cpu["cores"], kind="port",
                                    sample="2 steps x batch %d frames of the same workload, fp32 autograd oracle" % cpu["batch"])

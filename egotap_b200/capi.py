@@ -53,7 +53,7 @@ class Epilogue(C.Structure):
 
 class Gemm(C.Structure):
     _fields_ = [("a", Operand), ("b", Operand), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("groups", C.c_int), ("precision", C.c_int), ("variant", C.c_int), ("epi", Epilogue)]
+                ("groups", C.c_int), ("precision", C.c_int), ("variant", C.c_int), ("layout", C.c_int), ("epi", Epilogue)]
 
 
 _lib = None
@@ -238,9 +238,11 @@ def gemm(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_g
 
 
 def gemm_desc(a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0), a_rows=None,
-              b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
-    """the ``egotap_gemm`` descriptor for D = epi(A @ B^T) (no launch)"""
+              b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, tn=False, **epi):
+    """the ``egotap_gemm`` descriptor for D = epi(A @ B^T) (no launch); ``tn``: row-major operands with the contraction along
+    the rows, D[g] = A[gK:(g+1)K]^T @ B[gK:(g+1)K] (a_rows = b_rows = total rows; include/egotap_b200.h EGOTAP_GEMM_TN)"""
     d = Gemm()
+    d.layout = 1 if tn else 0
     d.a = Operand(_ptr(a_hi), _ptr(a_lo), lda or K, a_rows or M, *a_group)
     d.b = Operand(_ptr(b_hi), _ptr(b_lo), ldb or K, b_rows or N, *b_group)
     d.M, d.N, d.K, d.groups, d.precision, d.variant = M, N, K, groups, precision, variant

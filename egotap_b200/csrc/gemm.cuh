@@ -54,6 +54,11 @@ struct GemmShape {
   int gdiv;         // TMA coords: c2 = g % gdiv, c3 = g / gdiv
   int b_shared;     // 1: every group multiplies the same B matrix (B's group coordinates stay 0)
 };
+// TN = true (template): the operands are ROW-major with the CONTRACTION along the rows -- A[k][m], B[k][n], D = A^T B -- and a
+// group is a chunk of the contraction: D[g][m][n] = sum_{k < K} A[g K + k][m] B[g K + k][n].  This is the weight-gradient GEMM
+// dW = dY^T X straight from the row-major activations and gradients of the training step (no transposed copies): the TMA
+// boxes are 64 contraction rows x 64 columns and the MMA reads them through MN-major shared-memory descriptors
+// (canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in bf16 elements: LBO = one 8 KB box, SBO = 1 KB, 2 KB per k-step).
 
 // Per-thread row mapping of the epilogue (computed once per tile): output row, residual row, column shift.
 struct EpiRow {
@@ -282,7 +287,7 @@ __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const Ep
   __syncwarp();                 // the staging block is rewritten by the next chunk
 }
 
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false>
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false>
 struct GemmCfg {
   static constexpr int BM = 128;                     // rows per CTA (tile rows = BM * CG)
   static constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
@@ -306,12 +311,12 @@ struct GemmCfg {
   static_assert(BN == 32 * EPI_WARPS, "one epilogue thread per tile column (staging of the scale / bias vectors)");
 };
 
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false>
-__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL>::THREADS), 1)
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
-  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL>;
+  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN>;
   EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -362,7 +367,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::NOPS * C::A_BYTES;
-          if (CG == 1) {
+          if constexpr (TN) {
+            // 64 contraction rows x 64 columns per box: BM / 64 boxes of A, BNL / 64 boxes of B (8 KB each), group = row chunk
+            const int krow = g * s.K + kb * C::BK;
+            if (CG == 1 || cta_rank == 0) mbar_expect_tx(&full[stage], C::STAGE_BYTES * CG);
+#pragma unroll
+            for (int h = 0; h < C::BM / 64; ++h) {
+              if (CG == 1) tma_load_4d(sa + h * 8192, &tmAh, &full[stage], row_a + h * 64, krow, 0, 0);
+              else tma_load_4d_2sm(sa + h * 8192, &tmAh, &full[stage], row_a + h * 64, krow, 0, 0);
+              if (NSPLIT > 1) {
+                if (CG == 1) tma_load_4d(sa + C::A_BYTES + h * 8192, &tmAl, &full[stage], row_a + h * 64, krow, 0, 0);
+                else tma_load_4d_2sm(sa + C::A_BYTES + h * 8192, &tmAl, &full[stage], row_a + h * 64, krow, 0, 0);
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < C::BNL / 64; ++h) {
+              if (CG == 1) tma_load_4d(sb + h * 8192, &tmBh, &full[stage], row_b + h * 64, krow, 0, 0);
+              else tma_load_4d_2sm(sb + h * 8192, &tmBh, &full[stage], row_b + h * 64, krow, 0, 0);
+              if (NSPLIT > 1) {
+                if (CG == 1) tma_load_4d(sb + C::B_BYTES + h * 8192, &tmBl, &full[stage], row_b + h * 64, krow, 0, 0);
+                else tma_load_4d_2sm(sb + C::B_BYTES + h * 8192, &tmBl, &full[stage], row_b + h * 64, krow, 0, 0);
+              }
+            }
+          } else if (CG == 1) {
             mbar_expect_tx(&full[stage], C::STAGE_BYTES);
             tma_load_4d(sa, &tmAh, &full[stage], kb * C::BK, row_a, g0, g1);
             tma_load_4d(sb, &tmBh, &full[stage], kb * C::BK, row_b, bg0, bg1);
@@ -387,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(C::BM * CG, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(C::BM * CG, BN, TN ? 1 : 0, TN ? 1 : 0);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -399,16 +426,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           {
-            const uint32_t a_lo = sdesc_lo(smem_base + stage * C::STAGE_BYTES);
+            // K-major: 32 bytes per k-step inside the 128-byte rows; MN-major (TN): 16 contraction rows = 2 KB per k-step and
+            // LBO = one 8 KB box between 64-column groups
+            const uint32_t stage_addr = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t a_lo = TN ? (((stage_addr >> 4) & 0x3FFFu) | (uint32_t(8192 >> 4) << 16)) : sdesc_lo(stage_addr);
             constexpr uint32_t B_OFF = C::NOPS * C::A_BYTES;
+            constexpr int KSTEP = TN ? 2048 : 32;
 #pragma unroll
             for (int k = 0; k < C::BK / 16; ++k) {
-              const uint64_t dah = sdesc_at(a_lo, k * 32);
-              const uint64_t dbh = sdesc_at(a_lo, B_OFF + k * 32);
+              const uint64_t dah = sdesc_at(a_lo, k * KSTEP);
+              const uint64_t dbh = sdesc_at(a_lo, B_OFF + k * KSTEP);
               umma_bf16<CG>(d_tmem, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
               if (NSPLIT > 1) {
-                const uint64_t dal = sdesc_at(a_lo, C::A_BYTES + k * 32);
-                const uint64_t dbl = sdesc_at(a_lo, B_OFF + C::B_BYTES + k * 32);
+                const uint64_t dal = sdesc_at(a_lo, C::A_BYTES + k * KSTEP);
+                const uint64_t dbl = sdesc_at(a_lo, B_OFF + C::B_BYTES + k * KSTEP);
                 umma_bf16<CG>(d_tmem, dah, dbl, idesc, 1u);
                 umma_bf16<CG>(d_tmem, dal, dbh, idesc, 1u);
               }

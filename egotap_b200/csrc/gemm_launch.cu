@@ -9,10 +9,10 @@
 
 namespace eb {
 
-template <int CG, int BN, int NS, int ST, bool COAL = false>
+template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
-  using C = GemmCfg<CG, BN, NS, ST, COAL>;
-  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL>;
+  using C = GemmCfg<CG, BN, NS, ST, COAL, TN>;
+  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL, TN>;
   // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
@@ -36,15 +36,20 @@ struct Variant {
   int cg, bn, nsplit;
   int (*launch)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);
   int (*launch_coalesced)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);   // EGOTAP_EPI=coalesced
+  int (*launch_tn)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);          // D = A^T B (BN = 256 only)
 };
 
 static const Variant kVariants[] = {
-    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>},
-    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>},
-    {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>, &launch_variant<1, 256, 1, 4, true>},
-    {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>, &launch_variant<1, 256, 3, 2, true>},
-    {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>, &launch_variant<2, 256, 1, 6, true>},
-    {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>, &launch_variant<2, 256, 3, 3, true>},
+    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>, nullptr},
+    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>, nullptr},
+    {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>, &launch_variant<1, 256, 1, 4, true>,
+     &launch_variant<1, 256, 1, 4, true, true>},
+    {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>, &launch_variant<1, 256, 3, 2, true>,
+     &launch_variant<1, 256, 3, 2, true, true>},
+    {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>, &launch_variant<2, 256, 1, 6, true>,
+     &launch_variant<2, 256, 1, 6, true, true>},
+    {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>, &launch_variant<2, 256, 3, 3, true>,
+     &launch_variant<2, 256, 3, 3, true, true>},
 };
 static const int kNumVariants = int(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -64,6 +69,41 @@ int pick_variant(int M, int N, int groups, int nsplit) {
   const long long tiles2 = (long long)groups * ((M + 255) / 256) * ((N + 255) / 256);
   if (prefer_cg() == 2 && M >= 256 && tiles2 >= 16) return nsplit == 3 ? 5 : 4;
   return nsplit == 3 ? 3 : 2;
+}
+
+// D[g] = A[g K .. (g+1) K)^T B[g K .. (g+1) K): row-major operands with the contraction along the rows (GemmShape comment in
+// gemm.cuh); a.rows / b.rows = total rows of the matrices (reads beyond are zero-filled), a.ld / b.ld their row strides
+int gemm_tn_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, const EpiParams& ep, int nsplit, int variant,
+                cudaStream_t stream) {
+  EB_REQUIRE(s.M > 0 && s.N > 0 && s.K > 0 && s.groups > 0, "gemm(tn): bad shape M %d N %d K %d groups %d", s.M, s.N, s.K, s.groups);
+  EB_REQUIRE(s.K % 64 == 0 && s.N % 256 == 0 && s.M % 64 == 0, "gemm(tn): K %% 64, N %% 256, M %% 64 must be 0 (M %d N %d K %d)", s.M,
+             s.N, s.K);
+  EB_REQUIRE(nsplit == 1 || nsplit == 3, "gemm: nsplit must be 1 or 3");
+  EB_REQUIRE(a.hi && b.hi && (nsplit == 1 || (a.lo && b.lo)), "gemm(tn): null operand");
+  EB_REQUIRE(a.rows == b.rows && a.rows > 0, "gemm(tn): both operands have the contraction along their rows (a.rows %lld b.rows %lld)",
+             a.rows, b.rows);
+  if (variant < 0) {
+    const long long tiles2 = (long long)s.groups * ((s.M + 255) / 256) * (s.N / 256);
+    variant = (prefer_cg() == 2 && s.M >= 256 && tiles2 >= 16) ? (nsplit == 3 ? 5 : 4) : (nsplit == 3 ? 3 : 2);
+  }
+  EB_REQUIRE(variant >= 0 && variant < kNumVariants && kVariants[variant].launch_tn && kVariants[variant].nsplit == nsplit,
+             "gemm(tn): variant %d has no transposed-operand form for nsplit %d", variant, nsplit);
+  CUtensorMap tm[4];
+  int rc;
+  // contiguous extent = the M / N columns, rows = the contraction; boxes of 64 x 64
+  if ((rc = make_operand_tmap(&tm[0], a.hi, s.M, a.rows, a.ld, 1, 0, 1, 0, 64))) return rc;
+  if ((rc = make_operand_tmap(&tm[2], b.hi, s.N, b.rows, b.ld, 1, 0, 1, 0, 64))) return rc;
+  if (nsplit == 3) {
+    if ((rc = make_operand_tmap(&tm[1], a.lo, s.M, a.rows, a.ld, 1, 0, 1, 0, 64))) return rc;
+    if ((rc = make_operand_tmap(&tm[3], b.lo, s.N, b.rows, b.ld, 1, 0, 1, 0, 64))) return rc;
+  } else {
+    tm[1] = tm[0];
+    tm[3] = tm[2];
+  }
+  GemmShape sh = s;
+  sh.gdiv = 1;
+  ProfScope prof("gemm_tc_kernel", stream, s.M, s.N, s.K, s.groups, variant);
+  return kVariants[variant].launch_tn(tm, sh, ep, stream);
 }
 
 int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, const EpiParams& ep, int nsplit,
@@ -139,5 +179,7 @@ extern "C" int egotap_b200_gemm(const egotap_gemm* d, void* stream) {
   EB_REQUIRE(ep.out_f32 || ep.out_hi || (ep.store == STORE_QKV && ep.vt_hi), "gemm: no output pointer");
   EB_REQUIRE(ep.ldo % 8 == 0 && ep.col_off % 32 == 0, "gemm: ldo %% 8 and col_off %% 32 must be 0");
   const int nsplit = d->precision == EGOTAP_PREC_BF16 ? 1 : 3;
+  if (d->layout == EGOTAP_GEMM_TN) return gemm_tn_run(a, b, s, ep, nsplit, d->variant, (cudaStream_t)stream);
+  EB_REQUIRE(d->layout == EGOTAP_GEMM_NT, "gemm: unknown operand layout %d", d->layout);
   return gemm_run(a, b, s, ep, nsplit, d->variant, (cudaStream_t)stream);
 }

@@ -18,6 +18,8 @@ class StagedGradAllReduce:
         self.pending = []
         self._start = None
         self.launched = []          # (start, end) of every collective of the last step, for tests / logging
+        self.time_exposed = False   # bench: CUDA events around the wait in finish() = communication NOT hidden behind the backward
+        self._exposed = []
 
     def on_stage(self, i, start, end):
         """TrainEngine.backward callback: flat_grad[start:end] is final (in stream order)"""
@@ -33,6 +35,20 @@ class StagedGradAllReduce:
 
     def finish(self):
         """make the current stream (CPU: the caller) wait for every collective of this step"""
+        ev = None
+        if self.time_exposed and self.pending and self.engine.flat_grad.is_cuda:
+            import torch
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         for w in self.pending:
             w.wait()
+        if ev is not None:
+            ev[1].record()
+            self._exposed.append(ev)
         self.pending = []
+
+    def exposed_ms(self):
+        """mean time per step the compute stream spent waiting for the gradient all-reduces (call after a synchronize)"""
+        if not self._exposed:
+            return None
+        return sum(a.elapsed_time(b) for a, b in self._exposed) / len(self._exposed)

@@ -14,10 +14,11 @@ object is the ctypes binding (``capi.CudaBackend``); there is no CPU or PyTorch 
 
 Dataflow conventions
   * activations that feed a GEMM are bf16 "pairs" (hi, lo = bf16(x - hi)); lo is absent in the 'bf16' precision mode
-  * gradients flow in fp32; ``transpose_split`` turns a gradient into its row-major pair (A operand of the dX GEMM)
-    and its transposed pair (A operand of the dW GEMM) in one pass
-  * dW[n][k] = sum_r dY[r][n] X[r][k] runs as a split-K GEMM over the transposed copies dY^T (n x r) and X^T (k x r):
-    the reduction dimension r is cut into G chunks (GEMM groups), partial products are summed by ``reduce_partials``
+  * gradients flow in fp32; ``transpose_split`` turns a gradient into its row-major bf16 pair (and, in the same pass, applies
+    gelu' and forms the bias-gradient column sums)
+  * dW[n][k] = sum_r dY[r][n] X[r][k] runs as a split-K GEMM straight from the ROW-major pairs dY (r x n) and X (r x k) with the
+    contraction along the rows (EGOTAP_GEMM_TN: MN-major shared-memory descriptors, no transposed copies): r is cut into G
+    chunks (GEMM groups), partial products are summed by ``reduce_partials``
   * parameter gradients live in ONE flat fp32 buffer ordered by backward completion (``stages``), so data-parallel
     training all-reduces contiguous slices while earlier layers are still being differentiated
 """
@@ -184,20 +185,19 @@ class TrainEngine:
             epi["out_hi"], epi["out_lo"] = out.hi, out.lo
         self.be.gemm(A.hi, A.lo, W.hi, W.lo, M, N, K, lda=lda, ldb=ldb, precision=self.precision, **epi)
 
-    def _dw(self, dYt, Xt, n_out, k_out, rows, ld, grad):
-        """grad[n_out][k_out] = sum_r dY[r][n] X[r][k] from the transposed pairs dYt (n x ld), Xt (k x ld)"""
+    def _dw(self, dY, ldY, X, ldX, n_out, k_out, rows, grad):
+        """grad[n_out][k_out] = sum_r dY[r][n] X[r][k] from the row-major pairs dY (rows x n_out, row stride ldY) and
+        X (rows x k_out, row stride ldX); rows beyond ``rows`` are zero-filled by the TMA loads"""
         G, chunk = splitk(n_out, k_out, rows)
-        assert G * chunk <= ld
+        kw = dict(a_rows=rows, b_rows=rows, lda=ldY, ldb=ldX, precision=self.precision, tn=True, ldo=k_out)
         if G == 1:
-            self._gemm(dYt, ld, n_out, chunk, Xt, ld, k_out, out_f32=grad, ldo=k_out)
+            self.be.gemm(dY.hi, dY.lo, X.hi, X.lo, n_out, k_out, chunk, out_f32=grad, **kw)
             return
         need = G * n_out * k_out
         # sized once per batch size in _alloc: a recorded step (tape / CUDA graph) keeps raw device pointers, so no buffer
         # of the engine may be reallocated between _alloc calls
         assert self.partials is not None and self.partials.numel() >= need, "split-K scratch undersized (see _dw_shapes)"
-        self.be.gemm(dYt.hi, dYt.lo, Xt.hi, Xt.lo, n_out, k_out, chunk, groups=G, a_group=(G, chunk, 1, 0),
-                     b_group=(G, chunk, 1, 0), a_rows=n_out, b_rows=k_out, lda=ld, ldb=ld, precision=self.precision,
-                     out_f32=self.partials, ldo=k_out, group_rows=n_out)
+        self.be.gemm(dY.hi, dY.lo, X.hi, X.lo, n_out, k_out, chunk, groups=G, out_f32=self.partials, group_rows=n_out, **kw)
         self.be.reduce_partials(self.partials, G, n_out * k_out, grad)
 
     def _dw_shapes(self, B):
@@ -208,12 +208,10 @@ class TrainEngine:
         shapes += [(HID, MLPD, M), (MLPD, HID, M), (HID, HID, M), (HID, 256, Ml)]
         return shapes
 
-    def _tsplit(self, src, rows, cols, src_ld, rm, t, t_ld, rows_in=0, rows_out=0, bias=None, gelu_u=None):
-        """fp32 gradient -> row-major pair ``rm`` (rows x cols) and transposed pair ``t`` (cols x t_ld, zero padded);
-        in the same pass: multiply by gelu'(gelu_u) first, and the column sums (bias gradient) into ``bias``"""
-        self.be.transpose_split(src, rows, cols, src_ld, rows_in, rows_out,
-                                None if rm is None else rm.hi, None if rm is None else rm.lo, cols,
-                                None if t is None else t.hi, None if t is None else t.lo, t_ld, t_ld,
+    def _tsplit(self, src, rows, cols, src_ld, rm, rows_in=0, rows_out=0, bias=None, gelu_u=None):
+        """fp32 gradient -> row-major bf16 pair ``rm`` (rows x cols, row stride cols); in the same pass: multiply by
+        gelu'(gelu_u) first, and the column sums (bias gradient) into ``bias``"""
+        self.be.transpose_split(src, rows, cols, src_ld, rows_in, rows_out, rm.hi, rm.lo, cols, None, None, 0, 0,
                                 gelu_u, bias, None if bias is None else self.S["colpart"])
 
     def _tbf16(self, src, rows, cols, src_ld, dst, dst_ld, groups=(1, 0, 1, 0), dst_groups=(0, 0), pad=None):
@@ -331,9 +329,6 @@ class TrainEngine:
         S = self.S = {}
         S["dH"], S["dA"] = f32(M, HID), f32(M, MLPD)
         S["rm"] = pair(M, MLPD)                               # row-major bf16 copy of the current gradient
-        ldM, ldR, ldJ = pad_ld(M), pad_ld(R), pad_ld(RJ)
-        t_elems = max(MLPD * ldM, 16 * HID * ldR, 5 * PUH * ldJ)
-        S["TA"], S["TB"] = pair(1, t_elems), pair(1, t_elems)   # transposed gradient / transposed activation
         S["dctx"] = pair(M, HID)
         if fused:
             S["dsum"] = f32(B * HEADS * TOK)
@@ -469,8 +464,7 @@ class TrainEngine:
         be, P, A, S, WT, J, g = self.be, self.P, self.A, self.S, self.WT, self.J, self.grad
         B = self.batch
         M, R, RJ, live = B * TOK, B * self.n_hm, B * J, self.live
-        ldM, ldR, ldJ = pad_ld(M), pad_ld(R), pad_ld(RJ)
-        TA, TB, rm = S["TA"], S["TB"], S["rm"]
+        rm = S["rm"]
         v = "pos_heatmap_encoder.vit."
         pu = "skel_sequential_layer.lstm_custom.layers."
         if dpose is None:
@@ -498,34 +492,29 @@ class TrainEngine:
         self._chain_bwd(B, A["FG1"][:, PUH:], 5 * PUH, A["FG1"], 5 * PUH, A["C1"], A["skel"], S["dSkel"],
                         dFG1[:, PUH:], 5 * PUH, dFG1, 5 * PUH, WT["hh1"])
         bt = S["bias_tmp"]
-        self._tsplit(dFG1, RJ, 5 * PUH, 5 * PUH, rm, TA, ldJ, bias=bt)
+        self._tsplit(dFG1, RJ, 5 * PUH, 5 * PUH, rm, bias=bt)
         be.copy(g[pu + "1.x2f.bias"], bt[:PUH])
         be.copy(g[pu + "1.x2h.bias"], bt[PUH:])
         be.copy(g[pu + "1.h2h.bias"], bt[PUH:])
-        self._tbf16(A["h0b"], RJ, PUH, PUH, TB, ldJ)
-        self._dw(TA, TB, PUH, PUH, RJ, ldJ, g[pu + "1.x2f.weight"])
-        self._dw(_rows(TA, PUH, ldJ), TB, 4 * PUH, PUH, RJ, ldJ, g[pu + "1.x2h.weight"])
-        self._tbf16(A["HG1"], RJ, PUH, PUH, TB, ldJ)
-        self._dw(_rows(TA, PUH, ldJ), TB, 4 * PUH, PUH, RJ, ldJ, g[pu + "1.h2h.weight"])
+        self._dw(rm, 5 * PUH, A["h0b"], PUH, PUH, PUH, RJ, g[pu + "1.x2f.weight"])
+        self._dw(_cols(rm, PUH), 5 * PUH, A["h0b"], PUH, 4 * PUH, PUH, RJ, g[pu + "1.x2h.weight"])
+        self._dw(_cols(rm, PUH), 5 * PUH, A["HG1"], PUH, 4 * PUH, PUH, RJ, g[pu + "1.h2h.weight"])
         self._gemm(rm, 5 * PUH, RJ, 5 * PUH, WT["cat1"], 5 * PUH, PUH, out_f32=S["dH0"], ldo=PUH)
         dG0, dF0, dE = S["dG0"], S["dF0"], S["dE"]
         self._chain_bwd(B, A["G0"], 4 * PUH, A["F0"], PUH + PUX, A["C0"], A["H0"], S["dH0"], dG0, 4 * PUH, dF0, PUH + PUX,
                         WT["hh0"])
-        self._tsplit(dG0, RJ, 4 * PUH, 4 * PUH, rm, TA, ldJ, bias=g[pu + "0.x2h.bias"])
+        self._tsplit(dG0, RJ, 4 * PUH, 4 * PUH, rm, bias=g[pu + "0.x2h.bias"])
         be.copy(g[pu + "0.b2h.bias"], g[pu + "0.x2h.bias"])
         be.copy(g[pu + "0.h2h.bias"], g[pu + "0.x2h.bias"])
-        self._tbf16(A["xb"], RJ, 2 * PUX, 2 * PUX, TB, ldJ)
-        self._dw(TA, TB, 4 * PUH, PUX, RJ, ldJ, g[pu + "0.x2h.weight"])
-        self._dw(TA, _rows(TB, PUX, ldJ), 4 * PUH, PUX, RJ, ldJ, g[pu + "0.b2h.weight"])
-        self._tbf16(A["HG0"], RJ, PUH, PUH, TB, ldJ)
-        self._dw(TA, TB, 4 * PUH, PUH, RJ, ldJ, g[pu + "0.h2h.weight"])
+        self._dw(rm, 4 * PUH, A["xb"], 2 * PUX, 4 * PUH, PUX, RJ, g[pu + "0.x2h.weight"])                 # x half of [x | b']
+        self._dw(rm, 4 * PUH, _cols(A["xb"], PUX), 2 * PUX, 4 * PUH, PUX, RJ, g[pu + "0.b2h.weight"])      # gated-bridge half
+        self._dw(rm, 4 * PUH, A["HG0"], PUH, 4 * PUH, PUH, RJ, g[pu + "0.h2h.weight"])
         # dE += dG0 . [x2h | b2h]   (columns [:256] d x, [256:] d b')
         self._gemm(rm, 4 * PUH, RJ, 4 * PUH, WT["xb0"], 4 * PUH, 2 * PUX, resid=dE, resid_ld=2 * PUX, out_f32=dE,
                    ldo=2 * PUX)
         be.pu_bridge_gate_bwd(dE, 2 * PUX, A["F0"], PUH + PUX, PUH, A["E"], PUX, RJ, dF0, PUH + PUX)
-        self._tsplit(dF0, RJ, PUH + PUX, PUH + PUX, rm, TA, ldJ, bias=g[pu + "0.x2f.bias"])
-        self._tbf16(A["xb"], RJ, PUX, 2 * PUX, TB, ldJ)
-        self._dw(TA, TB, PUH + PUX, PUX, RJ, ldJ, g[pu + "0.x2f.weight"])
+        self._tsplit(dF0, RJ, PUH + PUX, PUH + PUX, rm, bias=g[pu + "0.x2f.bias"])
+        self._dw(rm, PUH + PUX, A["xb"], 2 * PUX, PUH + PUX, PUX, RJ, g[pu + "0.x2f.weight"])
         self._gemm(rm, PUH + PUX, RJ, PUH + PUX, WT["x2f0"], PUH + PUX, PUX, resid=dE, resid_ld=2 * PUX, out_f32=dE,
                    ldo=2 * PUX)
         done()
@@ -539,13 +528,12 @@ class TrainEngine:
                 y = A["%sy%d" % (e, i + 1)]
                 mean, rstd, scale, shift = (A["%s%s%d" % (e, s, i + 1)] for s in ("mean", "rstd", "scale", "shift"))
                 be.bn_bwd(da, y, R, n, scale, shift, mean, rstd, g[pre + "bn.weight"], g[pre + "bn.bias"], self.scr)
-                self._tsplit(da, R, n, n, rm, TA, ldR, bias=g[pre + "fc.bias"])
+                self._tsplit(da, R, n, n, rm, bias=g[pre + "fc.bias"])
                 if i == 0:
                     x_in, k = (A["fin"], 16 * HID) if e == "p" else (A["a_limb"], 8192)
                 else:
                     x_in, k = A["%sa%d" % (e, i)], (2048, 512)[i - 1]
-                self._tbf16(x_in, R, k, k, TB, ldR)
-                self._dw(TA, TB, n, k, R, ldR, g[pre + "fc.weight"])
+                self._dw(rm, n, x_in, k, n, k, R, g[pre + "fc.weight"])
                 if i > 0 or e == "p":
                     self._gemm(rm, n, R, n, WT["%sfc%d" % (e, i + 1)], n, k, out_f32=dn, ldo=k)
                     da, dn = dn, da
@@ -563,21 +551,18 @@ class TrainEngine:
             h_in, h_mid = A["h_in"][l], A["h_mid"][l]
             ln1, qk, vt, ctx, ln2, u, gl = (A[n][l] for n in ("ln1", "qk", "vt", "ctx", "ln2", "u", "g"))
             # MLP: h_out = h_mid + down(gelu(up(ln2)))
-            self._tsplit(dH, M, HID, HID, rm, TA, ldM, bias=g[p + "output.dense.bias"])
-            self._tbf16(gl, M, MLPD, MLPD, TB, ldM)
-            self._dw(TA, TB, HID, MLPD, M, ldM, g[p + "output.dense.weight"])
+            self._tsplit(dH, M, HID, HID, rm, bias=g[p + "output.dense.bias"])
+            self._dw(rm, HID, gl, MLPD, HID, MLPD, M, g[p + "output.dense.weight"])
             self._gemm(rm, HID, M, HID, WT["down%d" % l], HID, MLPD, out_f32=dA, ldo=MLPD)
             # d u = d g * gelu'(u), its bf16 copies and the bias gradient in one pass (d u is never stored in fp32)
-            self._tsplit(dA, M, MLPD, MLPD, rm, TA, ldM, bias=g[p + "intermediate.dense.bias"], gelu_u=u)
-            self._tbf16(ln2, M, HID, HID, TB, ldM)
-            self._dw(TA, TB, MLPD, HID, M, ldM, g[p + "intermediate.dense.weight"])
+            self._tsplit(dA, M, MLPD, MLPD, rm, bias=g[p + "intermediate.dense.bias"], gelu_u=u)
+            self._dw(rm, MLPD, ln2, HID, MLPD, HID, M, g[p + "intermediate.dense.weight"])
             self._gemm(rm, MLPD, M, MLPD, WT["up%d" % l], MLPD, HID, out_f32=dA, ldo=HID)
             be.layernorm_bwd(dA, h_mid, P[p + "layernorm_after.weight"], B, TOK, TOK, LN_EPS, dH, 1,
                              g[p + "layernorm_after.weight"], g[p + "layernorm_after.bias"], self.scr)
             # attention block: h_mid = h_in + o(attn(ln1))
-            self._tsplit(dH, M, HID, HID, rm, TA, ldM, bias=g[p + "attention.output.dense.bias"])
-            self._tbf16(ctx, M, HID, HID, TB, ldM)
-            self._dw(TA, TB, HID, HID, M, ldM, g[p + "attention.output.dense.weight"])
+            self._tsplit(dH, M, HID, HID, rm, bias=g[p + "attention.output.dense.bias"])
+            self._dw(rm, HID, ctx, HID, HID, HID, M, g[p + "attention.output.dense.weight"])
             dctx = S["dctx"]
             self._gemm(rm, HID, M, HID, WT["o%d" % l], HID, HID, out=dctx, ldo=HID)
             if self._alloc_fused:                            # dA <- d[Q | K | V]  (M x 3072)
@@ -585,23 +570,19 @@ class TrainEngine:
                 be.attention_bwd(qk.hi, vt.hi, dctx.hi, A["lse"][l], S["dsum"], dA, B)
             else:
                 self._attention_bwd(B, qk, vt, dctx, dA)
-            self._tsplit(dA, M, 3 * HID, 3 * HID, rm, TA, ldM, bias=S["dpos"])     # (3072,) sums into a spare buffer
+            self._tsplit(dA, M, 3 * HID, 3 * HID, rm, bias=S["dpos"])     # (3072,) sums into a spare buffer
             for q, n in enumerate(("query", "key", "value")):
                 be.copy(g[p + "attention.attention.%s.bias" % n], S["dpos"].view(-1)[q * HID:(q + 1) * HID])
-            self._tbf16(ln1, M, HID, HID, TB, ldM)
             for q, n in enumerate(("query", "key", "value")):
-                self._dw(_rows(TA, q * HID, ldM), TB, HID, HID, M, ldM, g[p + "attention.attention.%s.weight" % n])
+                self._dw(_cols(rm, q * HID), 3 * HID, ln1, HID, HID, HID, M, g[p + "attention.attention.%s.weight" % n])
             self._gemm(rm, 3 * HID, M, 3 * HID, WT["qkv%d" % l], 3 * HID, HID, out_f32=dA, ldo=HID)
             be.layernorm_bwd(dA, h_in, P[p + "layernorm_before.weight"], B, TOK, TOK, LN_EPS, dH, 1,
                              g[p + "layernorm_before.weight"], g[p + "layernorm_before.bias"], self.scr)
             done()
         # ---- embeddings: hidden[b, t] = patch_gemm + bias + pos_perm[t] (t < live) | mask_token + pos_perm[t]
         Ml = B * live
-        ldL = pad_ld(Ml)
-        self._tsplit(dH, Ml, HID, HID, None, TA, ldL, rows_in=TOK, rows_out=live,
-                     bias=g[v + "embeddings.patch_embeddings.projection.bias"])
-        self._tbf16(A["a_patch"], Ml, 256, 256, TB, ldL)
-        self._dw(TA, TB, HID, 256, Ml, ldL, g[v + "embeddings.patch_embeddings.projection.weight"])
+        self._tsplit(dH, Ml, HID, HID, rm, rows_in=TOK, rows_out=live, bias=g[v + "embeddings.patch_embeddings.projection.bias"])
+        self._dw(rm, HID, A["a_patch"], 256, HID, 256, Ml, g[v + "embeddings.patch_embeddings.projection.weight"])
         be.colsum(dH, B, TOK * HID, TOK * HID, 0, 0, S["dpos"], self.scr)      # sum over frames per token
         be.embed_grads(S["dpos"], self.grid, self.n_hm, g[v + "embeddings.position_embeddings"],
                        g[v + "embeddings.mask_token"])
@@ -752,9 +733,9 @@ def _offset(t, elems):
     return torch.as_strided(t, (n,), (1,), t.storage_offset() + elems)
 
 
-def _rows(pair, row, ld):
-    """rows [row:] of a transposed scratch pair laid out with leading dimension ld"""
-    return Pair(_offset(pair.hi, row * ld), None if pair.lo is None else _offset(pair.lo, row * ld))
+def _cols(pair, col):
+    """columns [col:] of a row-major pair (pointer offset; the caller keeps using the full matrix's row stride)"""
+    return Pair(_offset(pair.hi, col), None if pair.lo is None else _offset(pair.lo, col))
 
 
 def cosine_warmup_lr(step, base_lr, warmup_steps, total_steps):

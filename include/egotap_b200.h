@@ -79,11 +79,19 @@ typedef struct egotap_epilogue {
   int heads;              /* STORE_HEAD_MERGE: g = frame*heads + h -> row frame*tokens + m, col += h*N */
 } egotap_epilogue;
 
+/* operand layout.  NT (default): A[g][m][k], B[g][n][k], K contiguous -- D = A B^T.
+ * TN: A[k][m], B[k][n] row-major with the contraction along the ROWS and a group = a chunk of the contraction:
+ *   D[g][m][n] = sum_{k < K} A[g K + k][m] B[g K + k][n]   (the weight-gradient GEMM dW = dY^T X from row-major activations;
+ *   operand.rows = total rows of both matrices, reads beyond are zero-filled; group fields of the operands unused;
+ *   N % 256 == 0, M % 64 == 0; fp32 / bf16 outputs through the same epilogue, one (M x N) block per group). */
+enum { EGOTAP_GEMM_NT = 0, EGOTAP_GEMM_TN = 1 };
+
 typedef struct egotap_gemm {
   egotap_operand a, b;
   int M, N, K, groups;    /* per-group extents; K % 64 == 0, N % 32 == 0 */
   int precision;          /* EGOTAP_PREC_* */
   int variant;            /* -1 = auto; else index into the compiled tile configurations */
+  int layout;             /* EGOTAP_GEMM_* */
   egotap_epilogue epi;
 } egotap_gemm;
 

@@ -99,7 +99,7 @@ class OracleBackend:
 
     # ------------------------------------------------------------------ tcgen05 GEMM (csrc/gemm.cuh)
     def gemm(self, a_hi, a_lo, b_hi, b_lo, M, N, K, *, groups=1, a_group=(1, 0, 1, 0), b_group=(1, 0, 1, 0),
-             a_rows=None, b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, **epi):
+             a_rows=None, b_rows=None, lda=None, ldb=None, precision=PREC_BF16X3, variant=-1, tn=False, **epi):
         assert K % 64 == 0 and N % 32 == 0, (N, K)
         if precision == PREC_BF16X3:
             assert a_lo is not None and b_lo is not None
@@ -119,8 +119,20 @@ class OracleBackend:
             if rows < want_rows:            # TMA zero-fills rows beyond the tensor map's extent
                 x = torch.cat([x, x.new_zeros(groups, want_rows - rows, K)], 1)
             return x[:, :want_rows]
-        A = operand(a_hi, a_lo, lda or K, a_rows or M, a_group, M)
-        B = operand(b_hi, b_lo, ldb or K, b_rows or N, b_group, N)
+        if tn:
+            # row-major operands, contraction along the rows, group = chunk of K rows (EGOTAP_GEMM_TN); rows beyond a_rows are zero
+            assert a_rows == b_rows and N % 256 == 0 and M % 64 == 0
+
+            def chunks(hi, lo, ld, cols):
+                x = pair_f32(hi, lo, (a_rows, cols), (ld, 1))
+                pad = groups * K - a_rows
+                if pad > 0:
+                    x = torch.cat([x, x.new_zeros(pad, cols)], 0)
+                return x[:groups * K].reshape(groups, K, cols).transpose(1, 2)      # (groups, cols, K)
+            A, B = chunks(a_hi, a_lo, lda, M), chunks(b_hi, b_lo, ldb, N)
+        else:
+            A = operand(a_hi, a_lo, lda or K, a_rows or M, a_group, M)
+            B = operand(b_hi, b_lo, ldb or K, b_rows or N, b_group, N)
         # bf16x3 on the GPU is Ah*Bh + Ah*Bl + Al*Bh (the Al*Bl term, 2^-16 relative, is dropped); here the full
         # (Ah + Al)(Bh + Bl) product in fp32 stands for it
         acc = torch.matmul(A, B.transpose(1, 2))

@@ -216,7 +216,7 @@ inline void umma_bf16_now(int rank, uint32_t tmem_d, uint64_t adesc, uint64_t bd
   const int M = int((idesc >> 24) & 31) << 4, N = int((idesc >> 17) & 63) << 3;
   const uint32_t col = tmem_d & 0xFFFF, lane0 = tmem_d >> 16;
   const bool a_mn = ((idesc >> 15) & 1) != 0, b_mn = ((idesc >> 16) & 1) != 0;
-  if (col + N > 512 || lane0 != 0 || (CG != 1 && (a_mn || b_mn))) { fprintf(stderr, "ptx_emu: unsupported MMA (idesc %x tmem %x)\n", idesc, tmem_d); abort(); }
+  if (col + N > 512 || lane0 != 0) { fprintf(stderr, "ptx_emu: unsupported MMA (idesc %x tmem %x)\n", idesc, tmem_d); abort(); }
   static float A[256 * 16], B[256 * 16];
   if (CG == 1) {
     if (M != 128) { fprintf(stderr, "ptx_emu: cta_group::1 MMA with M = %d\n", M); abort(); }
@@ -227,8 +227,8 @@ inline void umma_bf16_now(int rank, uint32_t tmem_d, uint64_t adesc, uint64_t bd
   } else {
     if (M != 256 || rank != 0) { fprintf(stderr, "ptx_emu: cta_group::2 MMA must be issued by the leader with M = 256\n"); abort(); }
     for (int r = 0; r < 2; ++r) {       // A rows and B rows are split across the pair, at the same shared-memory offsets
-      emu_load_smem_operand(eb_emu::smem_of(r), adesc, 128, A + r * 128 * 16);
-      emu_load_smem_operand(eb_emu::smem_of(r), bdesc, N / 2, B + r * (N / 2) * 16);
+      emu_load_operand(eb_emu::smem_of(r), adesc, 128, a_mn, A + r * 128 * 16);
+      emu_load_operand(eb_emu::smem_of(r), bdesc, N / 2, b_mn, B + r * (N / 2) * 16);
     }
     for (int r = 0; r < 2; ++r) emu_mma_accumulate(eb_emu::tmem_of(r), 0, col, 128, N, A + r * 128 * 16, B, accumulate != 0);
   }

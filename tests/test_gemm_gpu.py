@@ -154,6 +154,31 @@ def test_fused_attention_matches_torch(x3, case):
     assert rel < tol, (case, x3, rel)
 
 
+@pytest.mark.parametrize("x3", [True, False])
+@pytest.mark.parametrize("shape", [(300, 320, 512, 3, 128), (7680, 2048, 512, 1, 7680), (147456 // 8, 1024, 1024, 6, 3072)])
+def test_gemm_transposed_operands(x3, shape):
+    """EGOTAP_GEMM_TN (csrc/gemm.cuh, TN = true): D[g] = A[gK:(g+1)K]^T B[gK:(g+1)K] from row-major operands with the contraction
+    along the rows -- MN-major shared-memory descriptors on both operands, 64 x 64 TMA boxes, ragged row count, column-slice
+    operands -- against torch fp64; the three shapes hit the cta_group::1 and paired-SM tiles and a split-K weight gradient"""
+    from egotap_b200 import capi
+    rows, M, N, G, Kc = shape
+    torch.manual_seed(rows)
+    ya = torch.randn(rows, M + 64, device="cuda")
+    xa = torch.randn(rows, N + 32, device="cuda")
+    yh, yl = capi.split_bf16(ya)
+    xh, xl = capi.split_bf16(xa)
+    part = torch.full((G * M, N), float("nan"), device="cuda")
+    capi.gemm(yh[:, 32:], yl[:, 32:] if x3 else None, xh, xl if x3 else None, M, N, Kc, groups=G, a_rows=rows, b_rows=rows, lda=M + 64,
+              ldb=N + 32, precision=capi.PREC_BF16X3 if x3 else capi.PREC_BF16, tn=True, out_f32=part, ldo=N, group_rows=M)
+    torch.cuda.synchronize()
+    a = (ya[:, 32:32 + M] if x3 else yh[:, 32:32 + M]).double()
+    b = (xa[:, :N] if x3 else xh[:, :N]).double()
+    ref = a.t() @ b
+    got = part.view(G, M, N).double().sum(0)
+    assert not torch.isnan(part).any()
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < (3e-5 if x3 else 1e-5)      # bf16: exact products, fp32 accumulation over up to 7,680 terms
+
+
 @pytest.mark.parametrize("case", ["normal", "wide_scores", "one_frame"])
 def test_fused_attention_backward_matches_autograd(case):
     """csrc/attention_bwd.cu (bf16-operand training mode): the forward's log-sum-exp output, attn_dsum and the two fused backward

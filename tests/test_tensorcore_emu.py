@@ -232,6 +232,30 @@ def test_gemm_grouped_operands(be, variant, prec):
     assert (outs[0] - dyt[:, :rows] @ xt[:, :rows].t()).abs().max() < (2e-3 if prec == 0 else 0.2)
 
 
+@pytest.mark.parametrize("variant,prec", [(2, 1), (3, 0), (4, 1), (5, 0)])
+def test_gemm_transposed_operands(be, variant, prec):
+    """EGOTAP_GEMM_TN: D[g] = A[gK:(g+1)K]^T B[gK:(g+1)K] from ROW-major operands with the contraction along the rows (the weight-
+    gradient GEMM without transposed copies): 64 x 64 TMA boxes, MN-major shared-memory descriptors on both operands, groups =
+    chunks of the contraction, ragged row count (zero fill), operands that are column slices of wider matrices"""
+    emu, orc = be
+    torch.manual_seed(60 + variant)
+    rows, M, N, G, Kc = 300, 320, 512, 3, 128                # 3 chunks of 128 rows cover 300 (84 zero-filled)
+    ya, xa = torch.randn(rows, M + 64), torch.randn(rows, N + 32)        # leading dimensions wider than the used columns
+    outs = []
+    for b_ in (emu.gemm_tc, orc.gemm):
+        yh, yl = _pairs(ya)
+        xh, xl = _pairs(xa)
+        part = torch.full((G * M, N), float("nan"))
+        kw = dict(groups=G, a_rows=rows, b_rows=rows, lda=M + 64, ldb=N + 32, precision=prec, tn=True, out_f32=part, ldo=N, group_rows=M)
+        if b_ is emu.gemm_tc:
+            kw["variant"] = variant
+        b_(yh[:, 32:], None if prec else yl[:, 32:], xh, None if prec else xl, M, N, Kc, **kw)
+        outs.append(part)
+    _close(outs[0], outs[1], 2e-5 if prec == 0 else 1e-6)
+    ref = (ya[:, 32:32 + M] if prec == 0 else ya[:, 32:32 + M].to(BF16).float()).t() @ (xa[:, :N] if prec == 0 else xa[:, :N].to(BF16).float())
+    assert (outs[0].view(G, M, N).sum(0) - ref).abs().max() < (2e-3 if prec == 0 else 1e-3)
+
+
 @pytest.mark.parametrize("prec", [1, 0])
 @pytest.mark.parametrize("variant", [""])
 def test_fused_attention_kernel(be, prec, variant):
