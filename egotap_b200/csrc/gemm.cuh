@@ -127,6 +127,7 @@ __device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* 
   }
 }
 
+template <bool RESID = true>
 __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
                                           const float4 (&t)[8], const float* sv_scale, const float* sv_bias, bool wide) {
   float v[32];
@@ -142,7 +143,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row,
   }
   const long long orow = row.orow;
   const int col = n0 + p.col_off + row.col_shift;
-  if (p.resid) {
+  if (RESID && p.resid) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       v[4 * j] += t[j].x; v[4 * j + 1] += t[j].y; v[4 * j + 2] += t[j].z; v[4 * j + 3] += t[j].w;
@@ -287,7 +288,10 @@ __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const Ep
   __syncwarp();                 // the staging block is rewritten by the next chunk
 }
 
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false>
+// EW16 = true: 16 epilogue warps instead of 8 (four per tensor-memory lane quarter, 64 columns each).  The row-domain epilogues
+// that only write bf16 operands (QKV, MLP-up + GELU) are bound by the latency of their own instruction stream with two warps per
+// scheduler (ncu: issue slots 35-47 % used, tensor pipe 55-75 %); four warps per scheduler hide it.  112 registers per thread.
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false>
 struct GemmCfg {
   static constexpr int BM = 128;                     // rows per CTA (tile rows = BM * CG)
   static constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
@@ -298,7 +302,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
   static constexpr int BAR_BYTES = 256;
   static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
-  static constexpr int EPI_WARPS = BN >= 256 ? 8 : 4;
+  static constexpr int EPI_WARPS = EW16 ? 16 : (BN >= 256 ? 8 : 4);
+  static_assert(!EW16 || (BN == 256 && !COAL), "16 epilogue warps: BN = 256, row-domain epilogue");
   static constexpr int VEC_BYTES = 2 * BN * 4;       // the tile's columns of the epilogue scale / bias vectors
   static constexpr int STG_BYTES = COAL ? EPI_WARPS * 4096 : 0;   // coalesced epilogue: one 32 x 32 fp32 block per warp
   static constexpr int VEC_OFF = STAGES * STAGE_BYTES + BAR_BYTES;
@@ -308,15 +313,15 @@ struct GemmCfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(BN == 32 * EPI_WARPS, "one epilogue thread per tile column (staging of the scale / bias vectors)");
+  static_assert(BN <= 32 * EPI_WARPS, "one epilogue thread per tile column (staging of the scale / bias vectors)");
 };
 
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false>
-__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN>::THREADS), 1)
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                const GemmShape s, const EpiParams ep) {
-  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN>;
+  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16>;
   EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -468,11 +473,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // this tile's columns of the scale / bias vectors: requested before the accumulator wait, staged in shared memory
         const int ncol = n_blk * BN + et;
         float my_scale = 1.0f, my_bias = 0.0f;
-        if (ep.scale != nullptr && ncol < s.N) my_scale = __ldg(ep.scale + ncol);
-        if (ep.bias != nullptr && ncol < s.N) my_bias = __ldg(ep.bias + ncol);
+        if (ep.scale != nullptr && et < BN && ncol < s.N) my_scale = __ldg(ep.scale + ncol);
+        if (ep.bias != nullptr && et < BN && ncol < s.N) my_bias = __ldg(ep.bias + ncol);
         named_bar_sync<32 * C::EPI_WARPS>(1);      // every epilogue warp has finished reading the previous tile's vectors
-        sv_scale[et] = my_scale;
-        sv_bias[et] = my_bias;
+        if (et < BN) {
+          sv_scale[et] = my_scale;
+          sv_bias[et] = my_bias;
+        }
       }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -521,6 +528,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         continue;
       }
+      if constexpr (EW16) {
+        // 16-warp form: launched only for epilogues without a residual (the launcher's policy), so none is compiled in
+#pragma unroll 1
+        for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
+          const int n0 = n_first + c * 32;
+          if (n0 >= s.N) break;
+          uint32_t r[32];
+          tmem_ld32(t_addr + col_base + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) epi_apply<false>(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide);
+        }
+      } else {
       if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur, wide);
 #pragma unroll 1
       for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
@@ -536,6 +555,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];
         }
+      }
       }
       tc_fence_before();
       __syncwarp();

@@ -9,10 +9,10 @@
 
 namespace eb {
 
-template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false>
+template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false, bool EW16 = false>
 static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
-  using C = GemmCfg<CG, BN, NS, ST, COAL, TN>;
-  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL, TN>;
+  using C = GemmCfg<CG, BN, NS, ST, COAL, TN, EW16>;
+  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL, TN, EW16>;
   // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
@@ -37,19 +37,20 @@ struct Variant {
   int (*launch)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);
   int (*launch_coalesced)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);   // EGOTAP_EPI=coalesced
   int (*launch_tn)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);          // D = A^T B (BN = 256 only)
+  int (*launch_ew16)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);        // row-domain epilogue on 16 warps
 };
 
 static const Variant kVariants[] = {
-    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>, nullptr},
-    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>, nullptr},
+    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>, nullptr, nullptr},
+    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>, nullptr, nullptr},
     {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>, &launch_variant<1, 256, 1, 4, true>,
-     &launch_variant<1, 256, 1, 4, true, true>},
+     &launch_variant<1, 256, 1, 4, true, true>, nullptr},
     {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>, &launch_variant<1, 256, 3, 2, true>,
-     &launch_variant<1, 256, 3, 2, true, true>},
+     &launch_variant<1, 256, 3, 2, true, true>, nullptr},
     {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>, &launch_variant<2, 256, 1, 6, true>,
-     &launch_variant<2, 256, 1, 6, true, true>},
+     &launch_variant<2, 256, 1, 6, true, true>, &launch_variant<2, 256, 1, 6, false, false, true>},
     {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>, &launch_variant<2, 256, 3, 3, true>,
-     &launch_variant<2, 256, 3, 3, true, true>},
+     &launch_variant<2, 256, 3, 3, true, true>, &launch_variant<2, 256, 3, 3, false, false, true>},
 };
 static const int kNumVariants = int(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -148,7 +149,15 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
     if (strcmp(epi_env, "coalesced") == 0) coalesced = true;
     else if (strcmp(epi_env, "rows") == 0) coalesced = false;
   }
-  return coalesced ? v.launch_coalesced(tm, sh, ep, stream) : v.launch(tm, sh, ep, stream);
+  if (coalesced) return v.launch_coalesced(tm, sh, ep, stream);
+  // row-domain epilogue: 16 warps for the GELU epilogue (MLP-up), where the math per element is long enough for four warps per
+  // scheduler to pay (measured, bf16 mode: 966 -> 1,060 TFLOP/s; the plain bf16 stores of QKV lose 6 % with 16 warps, the
+  // parity mode is indifferent: profiles/r02e_epilogue_warps.md).  EGOTAP_EPI_WARPS=8 / 16 forces one form (A/B).
+  static int ew = -1;
+  if (ew < 0) { const char* e = getenv("EGOTAP_EPI_WARPS"); ew = !e ? 0 : (e[0] == '8' ? 8 : 16); }
+  const bool want16 = ew == 16 || (ew == 0 && ep.act == ACT_GELU);
+  if (want16 && v.launch_ew16 && ep.resid == nullptr) return v.launch_ew16(tm, sh, ep, stream);
+  return v.launch(tm, sh, ep, stream);
 }
 
 }  // namespace eb
