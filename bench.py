@@ -230,7 +230,7 @@ def measure_lifting(ctx, args, preset, B, precision, workload="lifting", graph=F
     K, W = args.steps, args.warmup
     torch.manual_seed(0)                                   # reference-style random init (kaiming), same on every rank
     net = egotap_b200.EgoTAPAutoEncoder(make_opt(preset, b200_precision=precision, b200_max_batch=B,
-                                                 b200_cuda_graph=B if graph else 0), input_channel_scale=2)
+                                                 b200_cuda_graph=B if (graph and workload != "e2e_rgb") else 0), input_channel_scale=2)
     net.init_weights("kaiming")
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     net = net.to(dev).eval()
@@ -245,7 +245,8 @@ def measure_lifting(ctx, args, preset, B, precision, workload="lifting", graph=F
         pos_opt.num_rot_heatmap = 0
         rot_opt.num_heatmap = 0
         est = StereoPoseEstimator(HeatMapUNet(pos_opt).to(dev).to(memory_format=torch.channels_last),
-                                  HeatMapUNet(rot_opt).to(dev).to(memory_format=torch.channels_last), net).eval()
+                                  HeatMapUNet(rot_opt).to(dev).to(memory_format=torch.channels_last), net,
+                                  cuda_graph=bool(graph)).eval()
         g = torch.Generator().manual_seed(77 + rank)
         rgb_host = [torch.rand(B, 3, 256, 256, generator=g).pin_memory() for _ in range(2)]
         rgb = [t.to(dev) for t in rgb_host]
@@ -354,8 +355,12 @@ def measure_lifting(ctx, args, preset, B, precision, workload="lifting", graph=F
     pk = peaks()
     # rank 0 alone runs this extra step (the other ranks wait at the barrier): it must not contain a collective
     graph_batch, net._graph_max_batch = net._graph_max_batch, 0    # the per-kernel events need launched (not replayed) kernels
+    if est is not None:
+        est_graph, est.cuda_graph = est.cuda_graph, False
     all_recs = capi.profile_kernels(lambda: local_step())
     net._graph_max_batch = graph_batch
+    if est is not None:
+        est.cuda_graph = est_graph
     if graph:
         launches = K * len(all_recs)                                # kernels executed from the graph in the timed region
     recs = [r for r in all_recs if "flops" in r]

@@ -72,3 +72,29 @@ def test_end_to_end_rgb_to_pose_matches_staged_computation(state_dicts):
         ref = orc.forward(sd, hm, preset)
     rep = orc.parity_report(pose, ref)
     assert rep["rel"] <= 1e-3 and rep["mpjpe_delta_mm"] <= 0.1, rep      # includes cuDNN-vs-CPU conv differences
+
+
+@pytest.mark.gpu
+def test_pipeline_replayed_from_a_cuda_graph_equals_the_launched_one(state_dicts):
+    """StereoPoseEstimator(cuda_graph=True): both producers, the hand-off and the lifting kernels captured once per batch
+    shape and replayed -- same kernels on the same buffers, so the poses are bit-identical to the launched pipeline, also
+    for a second batch (inputs are copied into the graph's static buffers) and a second batch size"""
+    import egotap_b200
+    from egotap_b200.heatmap_net import HeatMapUNet, StereoPoseEstimator
+    preset = "EgoCap"
+    lift = egotap_b200.EgoTAPAutoEncoder(make_opt(preset), input_channel_scale=2)
+    lift.load_state_dict(state_dicts(preset))
+    pos_opt, rot_opt = make_opt(preset), make_opt(preset)
+    pos_opt.num_rot_heatmap = 0
+    rot_opt.num_heatmap = 0
+    torch.manual_seed(0)
+    hp, hr = HeatMapUNet(pos_opt), HeatMapUNet(rot_opt)
+    eager = StereoPoseEstimator(hp, hr, lift).cuda().eval()
+    graphed = StereoPoseEstimator(hp, hr, lift, cuda_graph=True).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    for batch in (2, 2, 3):
+        l, r = torch.rand(batch, 3, 256, 256, generator=g).cuda(), torch.rand(batch, 3, 256, 256, generator=g).cuda()
+        a = eager(l, r).clone()
+        b = graphed(l, r).clone()
+        assert torch.isfinite(a).all() and torch.equal(a, b), (batch, (a - b).abs().max().item())
+    assert len(graphed._graphs) == 2
