@@ -133,6 +133,9 @@ class StereoPoseEstimator(nn.Module):
     def _forward_graph(self, rgb_left, rgb_right):
         key = (tuple(rgb_left.shape), rgb_left.dtype, rgb_left.device)
         entry = self._graphs.get(key)
+        # a captured graph holds pointers into the lifting net's plan workspace: stale once the plan has been re-created
+        if entry is not None and entry[4] != getattr(self.net_AutoEncoder, "_plan_gen", 0):
+            entry = None
         if entry is None:
             sl, sr = torch.empty_like(rgb_left), torch.empty_like(rgb_right)
             sl.copy_(rgb_left)
@@ -146,8 +149,8 @@ class StereoPoseEstimator(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward(sl, sr)
-            entry = self._graphs[key] = (graph, sl, sr, out)
-        graph, sl, sr, out = entry
+            entry = self._graphs[key] = (graph, sl, sr, out, getattr(self.net_AutoEncoder, "_plan_gen", 0))
+        graph, sl, sr, out, _ = entry
         sl.copy_(rgb_left)
         sr.copy_(rgb_right)
         graph.replay()

@@ -251,6 +251,7 @@ class EgoTAPAutoEncoder(nn.Module):
         capi.check(lib.egotap_b200_plan_create(preset, self._precision, want, C.c_void_p(self._packed.data_ptr()),
                                                C.c_void_p(self._workspace.data_ptr()), C.byref(plan)), "plan_create")
         self._plan, self._plan_key, self._plan_batch = plan, key, want
+        self._plan_gen = getattr(self, "_plan_gen", 0) + 1       # anything that captured pointers into the old workspace is stale
         self._packed_versions = None
 
     def _destroy_plan(self):
