@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libegotap_b200.so")
+# EGOTAP_B200_LIB: A/B runs of two builds of the same library (tools/gpu_job_*.sh); never a non-CUDA path
+LIB_PATH = os.environ.get("EGOTAP_B200_LIB") or os.path.join(_HERE, "libegotap_b200.so")
 
 PREC_BF16X3, PREC_BF16 = 0, 1
 PRESET_ID = {"UnrealEgo": 0, "EgoCap": 1}

@@ -63,13 +63,13 @@ struct AttnWideCfg {
   // buffer is reloaded when the item's last score tile has been computed; the tile is prefetched into L2 an item ahead.
   static constexpr int QBUF = NSPLIT == 1 ? 2 : 1;
   static constexpr int BAR_OFF = QBUF * Q_BYTES + NSLOTS * GRAN_BYTES;
-  static constexpr int XCHG_OFF = BAR_OFF + 256;             // [2][2][128] row maxima, then [2][2][128] row sums
+  static constexpr int XCHG_OFF = BAR_OFF + 512;             // [2][2][128] row maxima, then [2][2][128] row sums
   static constexpr int SMEM_BYTES = XCHG_OFF + 5120;         // base must be 1 KB aligned (checked); + [2][128] final row maxima
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
   static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(2 * QBUF + 2 * NSLOTS + 10 + 1 <= 32, "barrier block");
+  static_assert(2 * QBUF + 2 * NSLOTS + 12 + 1 <= 64, "barrier block");
 };
 
 template <int NSPLIT>
@@ -93,7 +93,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
   uint64_t* pv_done = p_full + 2;           // [2]  PV_g finished: O up to date (needed only for a rescale of O)
   uint64_t* o_full = pv_done + 2;           // [2]  last PV of an item finished
   uint64_t* o_empty = o_full + 2;           // [2]  epilogue has drained that O buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* p_half = o_empty + 2;           // [2]  first 32 keys of every softmax warp's half of P_g in TMEM (full tiles)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
   float* xmax = reinterpret_cast<float*>(smem + C::XCHG_OFF);     // [2][2][128]
   float* lsum = xmax + 512;                                        // [2][2][128]
   float* mfin = lsum + 512;                                        // [2][128] reference maximum at the end of an item (for lse)
@@ -111,7 +112,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
     for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&p_half[i], 8);
     }
     fence_mbar_init();
   }
@@ -246,14 +247,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       const uint32_t t_o = C::T_O + uint32_t(it & 1) * AW_D;
       const uint32_t t_p = C::T_S + uint32_t(g & 1) * 128u;
       if (j == 0) TW_WAIT(5, mbar_wait(&o_empty[it & 1], ((it >> 1) & 1) ^ 1));   // the epilogue drained this O buffer (two items ago)
-      TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
-      const int ngran = j == AW_NT - 1 ? AW_LAST_KEYS / 64 : AW_KT / 64;
-      for (int kg = 0; kg < ngran; ++kg) {
-        uint32_t slot;
-        const uint32_t g_lo = slot_wait(slot);
-        tc_fence_after();
+      // P_g is handed over in two steps (full tiles): each softmax warp publishes the first 32 of its 64 keys (p_half), then the
+      // rest (p_full), so the k-steps over keys {0-31, 64-95} run while the exponentials of {32-63, 96-127} are still being
+      // computed -- the P V MMAs of a tile no longer wait for the whole softmax of that tile.
+      auto pv_steps = [&](uint32_t g_lo, int kg, int kk0, int kk1) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = kk0; kk < kk1; ++kk) {
           const uint64_t vh = sdesc_at(g_lo, kk * 32);
           const uint32_t pa = t_p + uint32_t(kg * 32 + kk * 8);      // 16 keys = 8 packed columns per k-step
           umma_bf16_ts(t_o, pa, vh, idesc_o, (j == 0 && kg == 0 && kk == 0) ? 0u : 1u);
@@ -263,6 +262,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
             umma_bf16_ts(t_o, pa + C::P_LO, vh, idesc_o, 1u);
           }
         }
+      };
+      if (j != AW_NT - 1) {
+        uint32_t slot0, slot1;
+        const uint32_t g0_lo = slot_wait(slot0);
+        const uint32_t g1_lo = slot_wait(slot1);
+        TW_WAIT(4, mbar_wait(&p_half[g & 1], (g >> 1) & 1));
+        tc_fence_after();
+        pv_steps(g0_lo, 0, 0, 2);
+        pv_steps(g1_lo, 1, 0, 2);
+        TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
+        tc_fence_after();
+        pv_steps(g0_lo, 0, 2, 4);
+        pv_steps(g1_lo, 1, 2, 4);
+        umma_commit<1>(&kv_empty[slot0]);
+        umma_commit<1>(&kv_empty[slot1]);
+      } else {                                  // 64-key tail tile: one V^T granule, every warp's 32 keys arrive at once
+        uint32_t slot;
+        const uint32_t g_lo = slot_wait(slot);
+        TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
+        tc_fence_after();
+        pv_steps(g_lo, 0, 0, 4);
         umma_commit<1>(&kv_empty[slot]);
       }
       umma_commit<1>(&pv_done[g & 1]);
@@ -346,6 +366,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         tmem_st16(t_s + pcol0, hh);
         if (NSPLIT > 1) tmem_st16(t_s + C::P_LO + pcol0, ll);
       }
+      // first 32 keys of this warp are in tensor memory: the issuing warp may start the P V k-steps that read them (every tile
+      // arrives here, so the barrier's phase follows the tile index also across the 64-key tail tiles)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_half[sb]);
       if (full_tile) {
         uint32_t hh[16], ll[16];
 #pragma unroll

@@ -131,8 +131,11 @@ def test_batch_sizes_and_ragged_batches(state_dicts):
     full = net.predict_pose(x).clone()
     one = net.predict_pose(x[3:4]).clone()
     part = net.predict_pose(x[:5]).clone()
-    assert (full[3:4] - one).abs().max().item() < 2e-5
-    assert (full[:5] - part).abs().max().item() < 2e-5
+    # not bit-identical: at <= 32 frames the first FC block is split along its reduction dimension into a batch-dependent number
+    # of chunks (fp32 summation order), which shows at the 1e-5 level of the fp32-parity mode (vs the oracle: ~1e-4)
+    scale = full.abs().max().item()
+    assert (full[3:4] - one).abs().max().item() < 5e-5 * scale
+    assert (full[:5] - part).abs().max().item() < 5e-5 * scale
     with torch.no_grad():
         ref = orc.forward(state_dicts(preset), x.cpu(), preset)
     assert orc.parity_report(full, ref)["rel"] <= 5e-4
