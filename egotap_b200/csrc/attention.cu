@@ -26,13 +26,34 @@
 //     while the softmax warps finish the current item.
 // Shared memory: Q tile (hi/lo; two of them in bf16 mode) + a ring of 32 KB granules (one 64-wide d block of a 128-key K tile, or one 64-key
 // block of a V^T tile), consumed in MMA order.
-//   warp 0   TMA producer      warp 1   MMA issuer      warps 2-9  softmax (pairs split the keys of a tile)
-//   warps 10-13  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
+//   warp 0   TMA producer      warps 1, 2   MMA issuers (even / odd key tiles)      warp 3   tensor-memory allocation
+//   warps 4-11  softmax (pairs split the keys of a tile)
+//   warps 12-15  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
+// Two issuing warps (round 2, ncu source page of the single-issuer kernel): every tcgen05.mma costs its issuing warp ~40 cycles
+// of election / descriptor / R2UR instructions against 64 cycles of tensor-pipe work per 128 x 128 x 16 MMA; with the 96 MMAs of
+// a parity-mode tile on ONE warp that warp was busy ~3,900 of the ~4,300 cycles of a tile period and stalled on the MMA queue
+// only 12 % of its time -- instruction issue, not the tensor pipe or the softmax, set the period.  Warp 1 now issues S_g and
+// P V_g of the even tiles, warp 2 of the odd tiles.  Each S/P buffer is touched by one thread's MMAs only, so S_{g+2} still
+// follows P V_g in that thread's program order (no buffer-free barrier); the accumulation order of O across the two threads
+// is enforced with the existing pv_done barriers (P V_{g+1} is issued after P V_g has completed, which it has long before
+// P_{g+1} arrives).
 #include "gemm.cuh"
 #include "host_util.cuh"
 #include "internal.h"
 
 namespace eb {
+
+// A/B builds (tools/gpu_job_r2*.sh): -DEB_ATTN_NO_REGSPLIT keeps the launch-time register allocation and the compiler's own
+// handling of the role constants
+#ifdef EB_ATTN_NO_REGSPLIT
+template <int N> __device__ __forceinline__ void aw_reg_dec() {}
+template <int N> __device__ __forceinline__ void aw_reg_inc() {}
+__device__ __forceinline__ int aw_pin(int v) { return v; }
+#else
+template <int N> __device__ __forceinline__ void aw_reg_dec() { warpgroup_reg_dec<N>(); }
+template <int N> __device__ __forceinline__ void aw_reg_inc() { warpgroup_reg_inc<N>(); }
+__device__ __forceinline__ int aw_pin(int v) { return pin_reg(v); }
+#endif
 
 // Debug-only wait-cycle accounting (tools/attn_trace.py builds a separate library with -DEB_ATTN_TRACE); no-ops otherwise.
 #ifdef EB_ATTN_TRACE
@@ -49,7 +70,7 @@ __device__ unsigned long long g_attn_trace[32];
 constexpr int AW_TOK = 576, AW_HEADS = 8, AW_D = 128, AW_QT = 128, AW_KT = 128;
 constexpr int AW_NT = (AW_TOK + AW_KT - 1) / AW_KT;          // 5 key tiles, the last one has 64 keys
 constexpr int AW_LAST_KEYS = AW_TOK - (AW_NT - 1) * AW_KT;   // 64
-constexpr int AW_THREADS = 64 + 256 + 128;                   // TMA + MMA warps, 8 softmax warps, 4 epilogue warps
+constexpr int AW_THREADS = 128 + 256 + 128;                  // TMA / 2 MMA / allocation warps, 8 softmax warps, 4 epilogue warps
 static_assert(AW_LAST_KEYS == 64, "the last key tile is issued with N = 64");
 
 template <int NSPLIT>
@@ -68,8 +89,12 @@ struct AttnWideCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t T_S = 0, T_O = 256;              // S/P buffer b at T_S + 128 b; O buffer ob at T_O + 128 ob
   static constexpr uint32_t P_LO = 64;                       // packed lo columns of P inside its S/P buffer
+  // registers per thread after the role split (launched with 128): TMA / MMA / allocation warpgroup, the two softmax warpgroups
+  // (64 score registers + 32 packed probabilities live at once: 128 spilled and re-derived its role constants), epilogue
+  static constexpr int REG_ISSUE = 96, REG_SOFTMAX = 152, REG_EPILOGUE = 112;
+  static_assert(128 * REG_ISSUE + 256 * REG_SOFTMAX + 128 * REG_EPILOGUE <= 65536, "register file");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(2 * QBUF + 2 * NSLOTS + 12 + 1 <= 64, "barrier block");
+  static_assert(2 * QBUF + 3 * NSLOTS + 12 + 1 <= 64, "barrier block");
 };
 
 template <int NSPLIT>
@@ -86,8 +111,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* q_full = bars;                  // [QBUF]
   uint64_t* q_empty = bars + C::QBUF;       // [QBUF]  last score tile of an item has been computed
-  uint64_t* kv_full = bars + 2 * C::QBUF;   // [NSLOTS]
-  uint64_t* kv_empty = kv_full + C::NSLOTS;
+  uint64_t* kv_full = bars + 2 * C::QBUF;   // [2][NSLOTS]: one set per issuing warp (below)
+  uint64_t* kv_empty = kv_full + 2 * C::NSLOTS;
   uint64_t* s_full = kv_empty + C::NSLOTS;  // [2]  S_g in TMEM
   uint64_t* p_full = s_full + 2;            // [2]  P_g in TMEM (over S_g)
   uint64_t* pv_done = p_full + 2;           // [2]  PV_g finished: O up to date (needed only for a rescale of O)
@@ -108,20 +133,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
     if (NSPLIT > 1) { tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmVl); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < C::QBUF; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }   // q_empty: one commit per issuing warp
+    for (int i = 0; i < C::NSLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_full[C::NSLOTS + i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&p_half[i], 8);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
+  if (warp == 3) tmem_alloc<1>(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (*tmem_slot != 0) __trap();            // the whole TMEM was allocated: base is column 0 by construction
 
+  // (each warpgroup re-sizes its registers at the top of its own branch: ptxas budgets the code that follows a setmaxnreg)
+  if (warp < 4) {
+  aw_reg_dec<C::REG_ISSUE>();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // ring order = MMA consumption order: K(0); then per global tile g: K(g+1), V(g).  Q is outside the ring.
@@ -152,11 +180,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
           if (NSPLIT > 1) tma_prefetch_4d(&tmQl, kb * 64, qt * AW_QT, h, b);
         }
       };
-      auto slot_acquire = [&](uint64_t*& full) -> uint8_t* {
+      // A granule's arrival is signalled on the barrier set of the warp that consumes it (tile parity).  With ONE set, a warp that
+      // consumes only every other filling of a slot would wait for "its" phase while the previous filling (the other warp's) is
+      // still in flight -- and mbarrier parity waits succeed at once when the barrier is a phase behind: seen on the B200 in the
+      // parity mode (4 slots, loads often late) as non-deterministic results and launch failures.  Per warp, every phase of its
+      // barriers is waited for in order.
+      auto slot_acquire = [&](uint64_t*& full, int g) -> uint8_t* {
         const uint32_t slot = rc % C::NSLOTS, ph = (rc / C::NSLOTS) & 1;
         ++rc;
         TW_WAIT(2, mbar_wait(&kv_empty[slot], ph ^ 1));
-        full = &kv_full[slot];
+        full = &kv_full[(g & 1) * C::NSLOTS + slot];
         mbar_expect_tx(full, C::GRAN_BYTES);
         return sRing + slot * C::GRAN_BYTES;
       };
@@ -166,7 +199,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         const int j = g % AW_NT;
         for (int kb = 0; kb < 2; ++kb) {
           uint64_t* full;
-          uint8_t* dst = slot_acquire(full);
+          uint8_t* dst = slot_acquire(full, g);
           tma_load_4d(dst, &tmQh, full, kb * 64, j * AW_KT, AW_HEADS + h, b);
           if (NSPLIT > 1) tma_load_4d(dst + C::BLK, &tmQl, full, kb * 64, j * AW_KT, AW_HEADS + h, b);
         }
@@ -178,7 +211,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         const int ngran = j == AW_NT - 1 ? AW_LAST_KEYS / 64 : AW_KT / 64;
         for (int kg = 0; kg < ngran; ++kg) {
           uint64_t* full;
-          uint8_t* dst = slot_acquire(full);
+          uint8_t* dst = slot_acquire(full, g);
           tma_load_4d(dst, &tmVh, full, j * AW_KT + kg * 64, bh * AW_D, 0, 0);
           if (NSPLIT > 1) tma_load_4d(dst + C::BLK, &tmVl, full, j * AW_KT + kg * 64, bh * AW_D, 0, 0);
         }
@@ -197,20 +230,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       }
       TW_FLUSH(16, true)
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (all lanes run the loop; the
-    // wrappers elect one lane).  Program order: S_0; { S_{g+1}; PV_g }.
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers (all lanes run the loop; the wrappers
+    // elect one lane).  Warp 1 owns the even global tiles, warp 2 the odd ones; program order of each: S_p; { PV_g; S_{g+2} }.
+    const int par = warp - 1;
     constexpr uint32_t idesc_s = make_idesc_bf16(AW_QT, AW_KT);
     constexpr uint32_t idesc_s_last = make_idesc_bf16(AW_QT, AW_LAST_KEYS);
     constexpr uint32_t idesc_o = make_idesc_bf16(AW_QT, AW_D);
     const uint32_t q_lo0 = sdesc_lo(smem_u32(sQ)), ring_lo = sdesc_lo(smem_u32(sRing));
-    uint32_t rc = 0;
     TW_DECL
-    auto slot_wait = [&](uint32_t& slot) -> uint32_t {
-      slot = rc % C::NSLOTS;
-      const uint32_t ph = (rc / C::NSLOTS) & 1;
-      ++rc;
-      TW_WAIT(2, mbar_wait(&kv_full[slot], ph));
+    // position of a tile's granules in the ring sequence K(0); { K(g+1); V(g) }: a full tile has two V^T granules, the 64-key
+    // tail tile of every item one
+    auto seq_k = [&](int g) -> uint32_t { return g == 0 ? 0u : uint32_t(2 + 4 * (g - 1) - (g - 1) / AW_NT); };
+    auto seq_v = [&](int g) -> uint32_t { return uint32_t(2 + 4 * g - g / AW_NT + (g + 1 < my_tiles ? 2 : 0)); };
+    uint32_t full_ph = 0;       // bit s: parity of this warp's next wait on its kv_full barrier of slot s
+    auto slot_wait = [&](uint32_t seq, uint32_t& slot) -> uint32_t {
+      slot = seq % C::NSLOTS;
+      TW_WAIT(2, mbar_wait(&kv_full[par * C::NSLOTS + slot], (full_ph >> slot) & 1u));
+      full_ph ^= 1u << slot;
       return ring_lo + ((slot * C::GRAN_BYTES) >> 4);
     };
     auto issue_s = [&](int g) {
@@ -219,11 +256,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       const uint32_t idesc = j == AW_NT - 1 ? idesc_s_last : idesc_s;
       const int qb = it % C::QBUF;
       const uint32_t q_lo = q_lo0 + ((qb * C::Q_BYTES) >> 4);
-      if (j == 0) TW_WAIT(1, mbar_wait(&q_full[qb], (it / C::QBUF) & 1));
+      // both warps read the item's Q tile (the buffer is not reloaded before both have committed q_empty, so the phase
+      // waited for is the current or the previous one of the barrier: no aliasing)
+      TW_WAIT(1, mbar_wait(&q_full[qb], (it / C::QBUF) & 1));
+      const uint32_t seq = seq_k(g);
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         uint32_t slot;
-        const uint32_t g_lo = slot_wait(slot);
+        const uint32_t g_lo = slot_wait(seq + kb, slot);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
@@ -240,7 +280,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         umma_commit<1>(&kv_empty[slot]);
       }
       umma_commit<1>(&s_full[g & 1]);
-      if (j == AW_NT - 1) umma_commit<1>(&q_empty[qb]);
+      // a commit covers the MMAs of its own thread: each warp releases Q after its last score tile of the item (j = 3 and 4)
+      if (j >= AW_NT - 2) umma_commit<1>(&q_empty[qb]);
     };
     auto issue_pv = [&](int g) {
       const int it = g / AW_NT, j = g % AW_NT;
@@ -263,11 +304,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
           }
         }
       };
+      const uint32_t seq = seq_v(g);
+      // O is accumulated by the MMAs of two threads: P V_{g-1} (the other warp's) must have completed.  The barrier cannot run
+      // ahead: its next phase is P V_{g+1}, which waits for this tile's.
+      auto order_after_previous_pv = [&]() {
+        if (g > 0) { TW_WAIT(3, mbar_wait(&pv_done[(g - 1) & 1], uint32_t((g - 1) >> 1) & 1u)); }
+      };
       if (j != AW_NT - 1) {
         uint32_t slot0, slot1;
-        const uint32_t g0_lo = slot_wait(slot0);
-        const uint32_t g1_lo = slot_wait(slot1);
+        const uint32_t g0_lo = slot_wait(seq, slot0);
+        const uint32_t g1_lo = slot_wait(seq + 1, slot1);
+        order_after_previous_pv();
+#ifndef EB_ATTN_NO_PHALF
         TW_WAIT(4, mbar_wait(&p_half[g & 1], (g >> 1) & 1));
+#else
+        TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
+#endif
         tc_fence_after();
         pv_steps(g0_lo, 0, 0, 2);
         pv_steps(g1_lo, 1, 0, 2);
@@ -279,7 +331,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
         umma_commit<1>(&kv_empty[slot1]);
       } else {                                  // 64-key tail tile: one V^T granule, every warp's 32 keys arrive at once
         uint32_t slot;
-        const uint32_t g_lo = slot_wait(slot);
+        const uint32_t g_lo = slot_wait(seq, slot);
+        order_after_previous_pv();
         TW_WAIT(4, mbar_wait(&p_full[g & 1], (g >> 1) & 1));
         tc_fence_after();
         pv_steps(g_lo, 0, 0, 4);
@@ -288,26 +341,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       umma_commit<1>(&pv_done[g & 1]);
       if (j == AW_NT - 1) umma_commit<1>(&o_full[it & 1]);
     };
-    if (my_tiles > 0) issue_s(0);
-    for (int g = 0; g < my_tiles; ++g) {
-      if (g + 1 < my_tiles) issue_s(g + 1);
+    if (par < my_tiles) issue_s(par);
+    for (int g = par; g < my_tiles; g += 2) {
       issue_pv(g);
+      if (g + 2 < my_tiles) issue_s(g + 2);
     }
-    TW_FLUSH(0, lane == 0)
-  } else if (warp < 10) {
+    TW_FLUSH(0, lane == 0 && warp == 1)
+  }   // warp 3 (allocation warp) has nothing to do between allocation and release
+  } else if (warp < 12) {
     // ------------------------------------------------------------------ softmax warps (8)
+    aw_reg_inc<C::REG_SOFTMAX>();
     // Warps w and w+4 own the same TMEM lane quarter (query rows) and split the keys of a tile into two halves; the
     // pair agrees on the row maximum through shared memory and a 64-thread named barrier -- which also separates the
     // pair's loads of S from its stores of P into the same columns.
-    const int q = warp & 3;                       // TMEM lane quarter
-    const int hf = (warp - 2) >> 2;               // key half handled by this warp
-    const int row = q * 32 + lane;                // query row inside the tile
+    const int q = aw_pin(warp & 3);              // TMEM lane quarter
+    const int hf = aw_pin((warp - 4) >> 2);      // key half handled by this warp
+    const int row = aw_pin(q * 32 + lane);       // query row inside the tile
+    const bool lane0 = aw_pin(lane == 0 ? 1 : 0) != 0;
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
     const float c = 0.08838834764831845f * 1.4426950408889634f;   // log2(e) / sqrt(128)
     float m_ref = 0.f, l = 0.f;
+    const int n_tiles = aw_pin(my_tiles);
     TW_DECL
 #pragma unroll 1
-    for (int g = 0; g < my_tiles; ++g) {
+    for (int g = 0; g < n_tiles; ++g) {
       const int it = g / AW_NT, j = g % AW_NT;
       const uint32_t sb = uint32_t(g & 1), par = uint32_t(g >> 1) & 1u;
       const uint32_t t_s = C::T_S + sb * 128u + lane_sel;
@@ -371,7 +428,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_half[sb]);
+      if (lane0) mbar_arrive(&p_half[sb]);
       if (full_tile) {
         uint32_t hh[16], ll[16];
 #pragma unroll
@@ -391,11 +448,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[sb]);
+      if (lane0) mbar_arrive(&p_full[sb]);
     }
-    TW_FLUSH(8, warp == 2 && lane == 0)
+    TW_FLUSH(8, warp == 4 && lane == 0)
   } else {
     // ------------------------------------------------------------------ epilogue warps (4): O / l -> ctx rows
+    aw_reg_dec<C::REG_EPILOGUE>();
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = uint32_t(q * 32) << 16;
@@ -444,12 +502,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
     }
-    TW_FLUSH(24, warp == 10 && lane == 0)
+    TW_FLUSH(24, warp == 12 && lane == 0)
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(0u, C::TMEM_COLS);
+  if (warp == 3) tmem_dealloc<1>(0u, C::TMEM_COLS);
 }
 
 template <int NSPLIT>

@@ -359,7 +359,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Residual rows of the tile this CTA will finish (fp32, read by the epilogue a whole main loop later) are prefetched into L2
+    // by all lanes before lane 0 starts the tile's operand loads: the epilogue warps keep only one 32-column chunk of residual
+    // loads in flight (4 KB per warp), which at DRAM latency capped the out-projection at ~2.5 TB/s of residual reads (ncu, round
+    // 2: 27 % of the epilogue's samples on the first residual FADD of a chunk); from L2 the same window sustains the HBM rate.
+#ifdef EB_GEMM_NO_RESID_PREFETCH     // A/B builds (tools/gpu_job_r2*.sh)
+    constexpr bool pf_enabled = false;
+#else
+    constexpr bool pf_enabled = true;
+#endif
+    const bool pf_resid = pf_enabled && ep.resid != nullptr && ep.resid_mod == 0 && ep.store != STORE_QKV && (ep.resid_ld & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0 && ((ep.col_off | s.N) & 3) == 0;
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int n_blk = tile % nN; const int t2 = tile / nN;
@@ -368,7 +379,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int bg0 = s.b_shared ? 0 : g0, bg1 = s.b_shared ? 0 : g1;
         const int row_a = m_blk * C::BM * CG + cta_rank * C::BM;
         const int row_b = n_blk * BN + cta_rank * C::BNL;
-        for (int kb = 0; kb < nK; ++kb) {
+        if (pf_resid) {
+          const int ncols = (s.N - n_blk * BN < BN) ? (s.N - n_blk * BN) : BN;
+#pragma unroll
+          for (int i = 0; i < C::BM / 32; ++i) {
+            const int m = row_a + i * 32 + lane;
+            if (m < s.M) {
+              const EpiRow row = epi_row(ep, g, m, s.N);
+              if ((row.col_shift & 3) == 0)
+                l2_prefetch_bulk(ep.resid + row.rrow * ep.resid_ld + n_blk * BN + ep.col_off + row.col_shift, uint32_t(ncols) * 4u);
+            }
+          }
+        }
+        // lane 0 issues the operand loads; the other lanes wait at the end of the tile so that the prefetch stays one tile ahead
+        for (int kb = 0; lane == 0 && kb < nK; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::NOPS * C::A_BYTES;
@@ -414,6 +438,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (pf_resid) __syncwarp();
       }
     }
   } else if (warp == 1) {

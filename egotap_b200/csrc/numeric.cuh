@@ -80,19 +80,22 @@ inline float rcp_approx(float x) { return 1.0f / x; }
 #endif
 
 // Exact-erf GELU, x * Phi(x), branch-free: Phi through the complementary error function of |x|/sqrt(2) in the
-// Abramowitz-Stegun 7.1.26 form (|erf error| <= 1.5e-7, i.e. fp32 rounding level; measured max |gelu error| 4.2e-7
-// over [-12, 12] against fp64, the same as an fp32 evaluation of 0.5*x*(1+erf(x/sqrt 2))).  Two MUFU + ~12 FMA-pipe
-// instructions and no divergence, vs. the two-branch libdevice erff.  Reference: ACT2FN['gelu'], modeling_vit.py:326.
+// Abramowitz-Stegun 7.1.26 form (|erf error| <= 1.5e-7, i.e. fp32 rounding level; measured max |gelu error| 3.3e-7
+// over [-12, 12] against fp64, the same as an fp32 evaluation of 0.5*x*(1+erf(x/sqrt 2))).
+//   gelu(x) = max(x, 0) - |x| * h(|x|),   h(a) = 0.5 erfc(a / sqrt 2) = (0.5 p(t)) t exp(-a^2 / 2),  t = 1 / (1 + 0.3275911 a / sqrt 2)
+// with s = a sqrt(log2(e) / 2) so that exp(-a^2 / 2) = 2^(-s^2): 11 FMA-pipe instructions + 2 MUFU and no divergence (the first
+// version spent 17 + 2: the GELU epilogue of the MLP-up GEMM is bound by its own instruction stream, profiles/r02e_epilogue_warps.md).
+// Reference: ACT2FN['gelu'], modeling_vit.py:326.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = p * t * ex2_approx(u * (u * -1.4426950408889634f));   // erfc(u)
-  const float phi = x < 0.f ? 0.5f * y : fmaf(-0.5f, y, 1.0f);
-  return x * phi;
+  const float a = fabsf(x);
+  const float s = a * 0.84932180028801904f;                       // sqrt(log2(e) / 2)
+  const float t = rcp_approx(fmaf(0.27273748087922248f, s, 1.0f));   // 0.3275911 / sqrt(log2(e))
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);               // the 7.1.26 coefficients, halved
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float te = t * ex2_approx(-s * s);
+  return fmaf(-a, p * te, fmaxf(x, 0.0f));
 }
 
 }  // namespace eb

@@ -143,6 +143,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 // L2 prefetch of a 4-D tile (no shared-memory destination, no barrier): a later tma_load_4d of the same box hits L2
+// L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -301,6 +305,19 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// Register re-allocation between the warpgroups (4 consecutive warps) of a warp-specialised kernel: every warp of the warpgroup
+// executes the same instruction; N is a multiple of 8 in [24, 256].  An increase blocks until other warpgroups have released enough.
+template <int N>
+__device__ __forceinline__ void warpgroup_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void warpgroup_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// Makes a warp-role constant opaque to ptxas, which otherwise re-derives it from S2R SR_TID.X inside hot loops (ncu: 12 % of
+// the softmax warps' samples sat on the scoreboard of such re-reads).  An empty asm statement disappears in PTX; a shuffle from
+// the own lane is an identity that cannot be re-materialised.  All lanes of the warp call it.
+__device__ __forceinline__ int pin_reg(int v) {
+  asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(v) : "r"(threadIdx.x & 31));
+  return v;
+}
 
 }  // namespace eb
 #endif  // EB_HOST_EMU

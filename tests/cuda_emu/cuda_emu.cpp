@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <algorithm>
 #include <memory>
+#include <deque>
 #include <vector>
 
 namespace eb_emu {
@@ -128,13 +129,32 @@ void warp_barrier() {
 }
 }  // namespace
 
-namespace { std::vector<std::function<void()>> deferred; }
+namespace {
+std::vector<std::function<void()>> deferred;
+// "late TMA" mode (emu_set_tma_latency): bulk-tensor loads complete a random number of scheduler rounds after issue (in issue
+// order), so protocols that only work while loads land promptly -- e.g. an mbarrier parity wait by a thread that has not seen
+// the barrier's previous phase complete -- fail here as they do on a busy GPU
+struct LateOp { std::function<void()> op; unsigned long long due; };
+std::deque<LateOp> late_ops;
+unsigned long long round_no = 0, tma_rng = 88172645463325252ull;
+int tma_latency_max = 0;
+}
 void defer(std::function<void()> op) { deferred.push_back(std::move(op)); }
+void defer_tma(std::function<void()> op) {
+  if (tma_latency_max <= 0) { defer(std::move(op)); return; }
+  tma_rng ^= tma_rng << 13; tma_rng ^= tma_rng >> 7; tma_rng ^= tma_rng << 17;
+  unsigned long long due = round_no + 1 + tma_rng % (unsigned long long)tma_latency_max;
+  if (!late_ops.empty() && late_ops.back().due > due) due = late_ops.back().due;
+  late_ops.push_back({std::move(op), due});
+}
 static void run_deferred() {
   // asynchronous operations (TMA, tcgen05.mma, tcgen05.commit) issued during the previous round complete now, in issue
   // order: a consumer that did not wait for them has already run on stale / poisoned data
+  ++round_no;
   for (size_t i = 0; i < deferred.size(); ++i) { deferred[i](); ++progress; }
   deferred.clear();
+  while (!late_ops.empty() && late_ops.front().due <= round_no) { late_ops.front().op(); late_ops.pop_front(); ++progress; }
+  if (!late_ops.empty()) ++progress;     // loads in flight: time passing is progress (not a deadlock)
 }
 void note_progress() { ++progress; }
 void yield_wait() { need_coop("a spinning wait"); yield(); }
@@ -330,6 +350,7 @@ void launch_ex(dim3 grid, dim3 block, int cluster, size_t dyn_smem_bytes, const 
     }
   }
   run_deferred();
+  while (!late_ops.empty()) { late_ops.front().op(); late_ops.pop_front(); }   // nothing may leak into the next launch
   in_coop = false;
   cur = nullptr;
 }
@@ -348,6 +369,10 @@ extern "C" long long emu_set_dry_run(int on) {
   eb_emu::dry_run = on;
   eb_emu::dry_launches = 0;
   return n;          // launches that were checked (not executed) since the last call
+}
+extern "C" void emu_set_tma_latency(int max_rounds, unsigned long long seed) {
+  eb_emu::tma_latency_max = max_rounds;
+  eb_emu::tma_rng = seed ? seed : 88172645463325252ull;
 }
 extern "C" void emu_set_schedule(int mode, unsigned long long seed) {
   eb_emu::sched_mode = mode;

@@ -49,6 +49,7 @@ bool any_sync(bool pred);
 void wait_phase(const void* mbar_first_word, unsigned parity);   // block until the mbarrier phase bit != parity
 void yield_wait();              // a spinning wait gives the other fibers a turn (and feeds the deadlock detector)
 void defer(std::function<void()> op);   // an asynchronous operation: runs at the start of the next scheduler round
+void defer_tma(std::function<void()> op);   // a TMA load: as defer(), or a random number of rounds later (emu_set_tma_latency)
 void note_progress();           // any state change another fiber may be waiting for
 uint8_t* dyn_smem();            // dynamic shared memory of the running CTA
 uint8_t* smem_of(int cta_rank); // ... of a CTA of the running cluster

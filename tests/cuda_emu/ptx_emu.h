@@ -104,7 +104,7 @@ inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0,
   const uint32_t doff = uint32_t(dst - eb_emu::dyn_smem());
   if (doff % 1024) { fprintf(stderr, "ptx_emu: TMA destination must be 1024-byte aligned for the 128B swizzle\n"); abort(); }
   for (uint32_t i = 0; i < tm.box_rows * 64; ++i) { const uint16_t nan = 0x7fc0; memcpy(dst + i * 2, &nan, 2); }
-  eb_emu::defer([=]() { tma_load_now(dst, &tm, bar, c0, c1, c2, c3); });
+  eb_emu::defer_tma([=]() { tma_load_now(dst, &tm, bar, c0, c1, c2, c3); });
 }
 inline void tma_prefetch_4d(const CUtensorMap*, int, int, int, int) {}   // L2 prefetch: no functional effect
 inline void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -269,6 +269,10 @@ inline void tmem_st_n(uint32_t taddr, const uint32_t* r, int n) {
 inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_n(taddr, r, 32); }
 inline void tmem_st16(uint32_t taddr, const uint32_t* r) { tmem_st_n(taddr, r, 16); }
 inline void tmem_st_wait() {}
+inline void l2_prefetch_bulk(const void*, uint32_t) {}
+template <int N> inline void warpgroup_reg_dec() {}
+template <int N> inline void warpgroup_reg_inc() {}
+inline int pin_reg(int v) { return v; }
 // TS form, cta_group::1: A (128 x 16 bf16) from tensor memory -- lane = row, 8 consecutive 32-bit columns, each holding
 // the K-elements (2c, 2c + 1) as a packed bf16 pair with the even one in the low half; B from shared memory
 inline void umma_bf16_ts_now(int rank, uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

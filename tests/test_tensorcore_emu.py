@@ -710,6 +710,28 @@ def test_tensor_core_kernels_do_not_depend_on_the_thread_schedule(be, mode):
         _set_schedule(0)
 
 
+@pytest.mark.parametrize("latency", [4, 11], ids=["late4", "late11"])
+def test_tensor_core_kernels_with_late_tma_loads(be, latency):
+    """TMA loads that land a random number of scheduler rounds after issue (in order): a consumer may then reach an mbarrier
+    wait while the barrier's PREVIOUS phase is still in flight, which a parity wait answers with "complete".  This is how the
+    first two-issuer attention kernel failed on the B200 in the parity mode only (one set of kv_full barriers shared by two
+    consuming warps, each seeing every other phase) while passing every prompt-load emulation run."""
+    import ctypes as C
+    lib = _emu_lib()
+    lib.emu_set_tma_latency.argtypes = [C.c_int, C.c_ulonglong]
+    try:
+        for seed in (7, 2024):
+            lib.emu_set_tma_latency(latency, seed)
+            test_fused_attention_kernel(be, 0, "")
+            test_fused_attention_kernel(be, 1, "")
+        lib.emu_set_tma_latency(latency, 99)
+        test_gemm_tile_configurations(be, 0, 1)
+        test_gemm_tile_configurations(be, 3, 0)
+        test_persistent_chain_kernel(5, 15, True)
+    finally:
+        lib.emu_set_tma_latency(0, 0)
+
+
 @pytest.mark.parametrize("frames,J,x3", [(5, 15, True), (150, 17, False), (260, 15, True)])
 def test_persistent_bptt_kernel(be, frames, J, x3):
     """pu_chain_bwd_kernel (one launch = BPTT over all joints of a layer, W_hh^T slices resident, one group barrier per

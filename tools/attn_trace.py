@@ -7,7 +7,7 @@ import glob
 _csrc = glob.glob(os.path.join(ROOT, "egotap_b200", "csrc", "*"))
 if not os.path.isfile(lib) or "--build" in sys.argv or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in _csrc):
     os.makedirs(os.path.dirname(lib), exist_ok=True)
-    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "pu_chain.cu", "pu_chain_bwd.cu",
+    src = [os.path.join(ROOT, "egotap_b200", "csrc", f) for f in ("api.cu", "kernels.cu", "gemm_launch.cu", "attention.cu", "attention_bwd.cu", "pu_chain.cu", "pu_chain_bwd.cu",
                                                                        "metrics.cu", "plan.cu", "train_ops.cu", "train_model.cu", "gt_heatmap.cu")]
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
                            "-DEB_ATTN_TRACE", "-o", lib] + src)
@@ -31,7 +31,10 @@ for prec, name in ((capi.PREC_BF16X3, "x3"), (capi.PREC_BF16, "bf16")):
     v = [x / 148.0 for x in out]
     items = Bf * 8 * 5 / 148.0
     print("== attention_kernel %s (cycles per CTA, %.1f items = %.1f key tiles per CTA)" % (name, items, 5 * items))
-    print(" MMA warp : total %.0f | wait q_full %.0f  kv_full %.0f  p_full %.0f  o_empty %.0f | per tile %.0f" % (v[0], v[1], v[2], v[4], v[5], v[0] / items / 5))
+    # warp 1 issues the even tiles (half of them): its busy time per issued tile = (total - waits) / (tiles / 2)
+    waits = v[1] + v[2] + v[3] + v[4] + v[5]
+    print(" MMA warp 1 : total %.0f | wait q_full %.0f  kv_full %.0f  pv_done %.0f  p_half/p_full %.0f  o_empty %.0f | period per tile %.0f, busy per own tile %.0f"
+          % (v[0], v[1], v[2], v[3], v[4], v[5], v[0] / items / 5, (v[0] - waits) / (items * 2.5)))
     print(" softmax (warp 2) : total %.0f | wait s_full %.0f  pair_sync %.0f  pv_done(rescale) %.0f" % (v[8], v[9], v[10], v[11]))
     print(" producer : total %.0f | wait q_empty %.0f  kv_empty %.0f" % (v[16], v[17], v[18]))
     print(" epilogue : total %.0f | wait o_full %.0f" % (v[24], v[25]))
