@@ -48,6 +48,12 @@ struct EpiParams {
   int heads;
 };
 
+// Tensor maps of the TMA epilogue (TEPI): the fp32 output and the fp32 residual / additive table, described as bf16 matrices
+// of twice the width (a 64 x 32 box of bf16 = 32 fp32 columns x 32 rows = one warp's accumulator chunk).
+struct EpiMaps {
+  CUtensorMap out, res;
+};
+
 struct GemmShape {
   int M, N, K;      // per group
   int groups;       // tiles enumerate (g, m_blk, n_blk), n fastest
@@ -291,7 +297,16 @@ __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const Ep
 // EW16 = true: 16 epilogue warps instead of 8 (four per tensor-memory lane quarter, 64 columns each).  The row-domain epilogues
 // that only write bf16 operands (QKV, MLP-up + GELU) are bound by the latency of their own instruction stream with two warps per
 // scheduler (ncu: issue slots 35-47 % used, tensor pipe 55-75 %); four warps per scheduler hide it.  112 registers per thread.
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false>
+//
+// TEPI = true: TMA epilogue for fp32 outputs (residual stream, patch embedding, fp32 partial products).  The coalesced form above
+// still executes ~450 instructions per 32 x 32 chunk and keeps only one chunk of residual loads (4 KB per warp) in flight: at
+// K = 1024 in bf16 mode the epilogue needed ~21,000 cycles per tile against 8,192 of main loop (ncu, round 2: out-projection at
+// 43 % tensor-pipe activity).  Here each epilogue warp owns a ring of NBOX 4 KB boxes: the residual chunk arrives by TMA
+// (issued NBOX - 1 chunks ahead, across tile boundaries, i.e. normally a whole main loop ahead), the thread that owns row r adds
+// its accumulator row in place (the 128-byte-swizzle position of a 16-byte piece depends on the row only: no bank conflicts, no
+// cross-lane exchange) and one lane stores the box by TMA.  No global load / store instruction is left in the epilogue.
+// Eligibility (host, gemm_launch.cu): row-major fp32 output only, 32-row boxes map to 32 consecutive output / residual rows.
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false, bool TEPI = false>
 struct GemmCfg {
   static constexpr int BM = 128;                     // rows per CTA (tile rows = BM * CG)
   static constexpr int BK = 64;                      // bf16 elements = one 128-byte swizzle row
@@ -300,7 +315,7 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BNL * BK * 2;
   static constexpr int STAGE_BYTES = NOPS * (A_BYTES + B_BYTES);
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = TEPI ? 512 : 256;  // TEPI: + one mbarrier per epilogue warp and box (second half)
   static constexpr int TMEM_COLS = 2 * BN;           // double-buffered fp32 accumulator
   static constexpr int EPI_WARPS = EW16 ? 16 : (BN >= 256 ? 8 : 4);
   static_assert(!EW16 || (BN == 256 && !COAL), "16 epilogue warps: BN = 256, row-domain epilogue");
@@ -308,7 +323,11 @@ struct GemmCfg {
   static constexpr int STG_BYTES = COAL ? EPI_WARPS * 4096 : 0;   // coalesced epilogue: one 32 x 32 fp32 block per warp
   static constexpr int VEC_OFF = STAGES * STAGE_BYTES + BAR_BYTES;
   static constexpr int STG_OFF = VEC_OFF + VEC_BYTES;
-  static constexpr int SMEM_BYTES = STG_OFF + STG_BYTES;           // the dynamic shared memory is declared 1 KB aligned
+  static constexpr int NBOX = TEPI ? (NSPLIT == 1 ? 3 : 1) : 0;   // boxes per epilogue warp (what fits next to the operand ring)
+  static constexpr int BOX_OFF = (STG_OFF + STG_BYTES + 1023) / 1024 * 1024;
+  static constexpr int BOX_BYTES = EPI_WARPS * NBOX * 4096;
+  static constexpr int SMEM_BYTES = TEPI ? BOX_OFF + BOX_BYTES : STG_OFF + STG_BYTES;   // the dynamic shared memory is declared 1 KB aligned
+  static_assert(!TEPI || (!COAL && !TN && !EW16), "TMA epilogue: own form");
   static constexpr int COLS_PER_EPI_GROUP = BN / (EPI_WARPS / 4);
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
@@ -316,12 +335,12 @@ struct GemmCfg {
   static_assert(BN <= 32 * EPI_WARPS, "one epilogue thread per tile column (staging of the scale / bias vectors)");
 };
 
-template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false>
-__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16>::THREADS), 1)
+template <int CG, int BN, int NSPLIT, int STAGES, bool COAL = false, bool TN = false, bool EW16 = false, bool TEPI = false>
+__global__ void __launch_bounds__((GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16, TEPI>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               const GemmShape s, const EpiParams ep) {
-  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16>;
+               const GemmShape s, const EpiParams ep, const __grid_constant__ EpiMaps maps) {
+  using C = GemmCfg<CG, BN, NSPLIT, STAGES, COAL, TN, EW16, TEPI>;
   EB_DYN_SMEM_1K(smem);
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128-byte-swizzle tiles need a 1 KB aligned base
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
@@ -342,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   const int num_tiles = s.groups * nM * nN;
 
   if (warp == 0 && lane == 0) {
+    if constexpr (TEPI) { tma_prefetch_desc(&maps.out); tma_prefetch_desc(&maps.res); }
     tma_prefetch_desc(&tmAh);
     tma_prefetch_desc(&tmBh);
     if (NSPLIT > 1) { tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmBl); }
@@ -349,6 +369,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C::EPI_WARPS * CG); }
+    if constexpr (TEPI) {
+      uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + 256);
+      for (int i = 0; i < C::EPI_WARPS * C::NBOX; ++i) mbar_init(&rbar[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
@@ -359,18 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    // Residual rows of the tile this CTA will finish (fp32, read by the epilogue a whole main loop later) are prefetched into L2
-    // by all lanes before lane 0 starts the tile's operand loads: the epilogue warps keep only one 32-column chunk of residual
-    // loads in flight (4 KB per warp), which at DRAM latency capped the out-projection at ~2.5 TB/s of residual reads (ncu, round
-    // 2: 27 % of the epilogue's samples on the first residual FADD of a chunk); from L2 the same window sustains the HBM rate.
-#ifdef EB_GEMM_NO_RESID_PREFETCH     // A/B builds (tools/gpu_job_r2*.sh)
-    constexpr bool pf_enabled = false;
-#else
-    constexpr bool pf_enabled = true;
-#endif
-    const bool pf_resid = pf_enabled && ep.resid != nullptr && ep.resid_mod == 0 && ep.store != STORE_QKV && (ep.resid_ld & 3) == 0 &&
-                          (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0 && ((ep.col_off | s.N) & 3) == 0;
-    {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int n_blk = tile % nN; const int t2 = tile / nN;
@@ -379,20 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const int bg0 = s.b_shared ? 0 : g0, bg1 = s.b_shared ? 0 : g1;
         const int row_a = m_blk * C::BM * CG + cta_rank * C::BM;
         const int row_b = n_blk * BN + cta_rank * C::BNL;
-        if (pf_resid) {
-          const int ncols = (s.N - n_blk * BN < BN) ? (s.N - n_blk * BN) : BN;
-#pragma unroll
-          for (int i = 0; i < C::BM / 32; ++i) {
-            const int m = row_a + i * 32 + lane;
-            if (m < s.M) {
-              const EpiRow row = epi_row(ep, g, m, s.N);
-              if ((row.col_shift & 3) == 0)
-                l2_prefetch_bulk(ep.resid + row.rrow * ep.resid_ld + n_blk * BN + ep.col_off + row.col_shift, uint32_t(ncols) * 4u);
-            }
-          }
-        }
-        // lane 0 issues the operand loads; the other lanes wait at the end of the tile so that the prefetch stays one tile ahead
-        for (int kb = 0; lane == 0 && kb < nK; ++kb) {
+        for (int kb = 0; kb < nK; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::NOPS * C::A_BYTES;
@@ -438,7 +438,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (pf_resid) __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -490,6 +489,117 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     float* sv_scale = reinterpret_cast<float*>(smem + C::VEC_OFF);
     float* sv_bias = sv_scale + BN;
     int it = 0;
+    if constexpr (TEPI) {
+      constexpr int NCH = C::COLS_PER_EPI_GROUP / 32;           // chunks of this warp per tile
+      uint8_t* box0 = smem + C::BOX_OFF + (warp - 2) * C::NBOX * 4096;
+      uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + 256) + (warp - 2) * C::NBOX;
+      const bool has_resid = ep.resid != nullptr;
+      // this warp's 32 x 32 boxes of a tile: first tile row, first column, number of boxes inside the matrix, group
+      auto tile_boxes = [&](int tile, int& g, int& m0, int& n_first) -> int {
+        const int n_blk = tile % nN; const int t2 = tile / nN;
+        const int m_blk = t2 % nM;   g = t2 / nM;
+        m0 = m_blk * C::BM * CG + cta_rank * C::BM + q * 32;
+        n_first = n_blk * BN + col_base;
+        if (m0 >= s.M || n_first >= s.N) return 0;
+        const int left = (s.N - n_first) / 32;
+        return left < NCH ? left : NCH;
+      };
+      // residual boxes are requested NBOX - 1 chunks ahead of their use, along the sequence of this warp's chunks over all its tiles
+      int pf_tile = cluster_id, pf_c = 0, pf_nc = 0, pf_g = 0, pf_m0 = 0, pf_nf = 0;
+      uint32_t pf_n = 0, n = 0;
+      auto pf_settle = [&]() {
+        while (pf_tile < num_tiles) {
+          if (pf_c == 0) pf_nc = tile_boxes(pf_tile, pf_g, pf_m0, pf_nf);
+          if (pf_c < pf_nc) return;
+          pf_tile += num_clusters; pf_c = 0;
+        }
+      };
+      auto prefetch_to = [&](uint32_t limit) {      // requests the residual boxes of chunks [pf_n, limit)
+        while (pf_n < limit && pf_tile < num_tiles) {
+          if (lane == 0) {
+            const EpiRow row = epi_row(ep, pf_g, pf_m0, s.N);
+            const uint32_t slot = pf_n % C::NBOX;
+            mbar_expect_tx(&rbar[slot], 4096);
+            tma_load_4d(box0 + slot * 4096, &maps.res, &rbar[slot], 2 * (pf_nf + pf_c * 32 + ep.col_off), int(row.rrow), 0, 0);
+          }
+          ++pf_n; ++pf_c;
+          pf_settle();
+        }
+      };
+      pf_settle();
+      if (has_resid) prefetch_to(C::NBOX - 1);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int n_blk = tile % nN;
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        {
+          const int ncol = n_blk * BN + et;
+          float my_scale = 1.0f, my_bias = 0.0f;
+          if (ep.scale != nullptr && et < BN && ncol < s.N) my_scale = __ldg(ep.scale + ncol);
+          if (ep.bias != nullptr && et < BN && ncol < s.N) my_bias = __ldg(ep.bias + ncol);
+          named_bar_sync<32 * C::EPI_WARPS>(1);
+          if (et < BN) { sv_scale[et] = my_scale; sv_bias[et] = my_bias; }
+        }
+        mbar_wait(&tfull[as], aph);
+        tc_fence_after();
+        named_bar_sync<32 * C::EPI_WARPS>(1);
+        int g, m0, n_first;
+        const int nc = tile_boxes(tile, g, m0, n_first);
+        const EpiRow row0 = epi_row(ep, g, m0 < s.M ? m0 : 0, s.N);
+        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c, ++n) {
+          const int n0 = n_first + c * 32;
+          const uint32_t slot = n % C::NBOX;
+          uint32_t r[32];
+          tmem_ld32(t_addr + col_base + c * 32, r);
+          tmem_ld_wait();
+          if (c == nc - 1) {                    // the accumulator buffer is free once its last chunk is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]); }
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+          epi_scale_bias(ep, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, v);
+          if (ep.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (ep.act == ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+          }
+          // the box that takes chunk n + NBOX - 1 is the one chunk n - 1 was stored from: its store must have read it
+          if (lane == 0) { if (has_resid) bulk_wait_read<0>(); else bulk_wait_read<C::NBOX - 1>(); }
+          __syncwarp();
+          if (has_resid) {
+            prefetch_to(n + C::NBOX);
+            mbar_wait(&rbar[slot], (n / C::NBOX) & 1);
+          }
+          float4* rowp = reinterpret_cast<float4*>(box0 + slot * 4096 + lane * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            float4* pp = rowp + (j ^ (lane & 7));           // 128-byte swizzle: 16-byte piece j of row r sits at piece j ^ (r & 7)
+            if (has_resid) { const float4 t = *pp; x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
+            *pp = x;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&maps.out, box0 + slot * 4096, 2 * (n0 + ep.col_off), int(row0.orow), 0, 0);
+            bulk_commit();
+          }
+        }
+        if (nc == 0) {                          // a warp whose rows / columns lie outside the matrix still hands the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]); }
+        }
+      }
+      if (lane == 0) bulk_wait<0>();
+      __syncwarp();
+    } else {
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int n_blk = tile % nN; const int t2 = tile / nN;
       const int m_blk = t2 % nM;   const int g = t2 / nM;
@@ -588,6 +698,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         if (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
       }
     }
+    }   // !TEPI
   }
 
   tc_fence_before();

@@ -9,10 +9,12 @@
 
 namespace eb {
 
-template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false, bool EW16 = false>
-static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
-  using C = GemmCfg<CG, BN, NS, ST, COAL, TN, EW16>;
-  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL, TN, EW16>;
+static EpiMaps g_no_maps;      // kernels without the TMA epilogue never look at their map argument
+
+template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false, bool EW16 = false, bool TEPI = false>
+static int launch_variant_maps(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, const EpiMaps& maps, cudaStream_t stream) {
+  using C = GemmCfg<CG, BN, NS, ST, COAL, TN, EW16, TEPI>;
+  auto kern = gemm_tc_kernel<CG, BN, NS, ST, COAL, TN, EW16, TEPI>;
   // the opt-in to > 48 KB dynamic shared memory is a per-device function attribute
   static bool attr_done[64] = {false};
   const int dev_ = current_device();
@@ -26,9 +28,13 @@ static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiPa
   long long nclusters = num_sms() / CG;
   if (tiles < nclusters) nclusters = tiles;
   EB_CUDA(EB_LAUNCH_CLUSTER(kern, (unsigned)(nclusters * CG), C::THREADS, C::SMEM_BYTES, CG, stream, tm[0], tm[1], tm[2], tm[3],
-                            s, ep));
+                            s, ep, maps));
   EB_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
+}
+template <int CG, int BN, int NS, int ST, bool COAL = false, bool TN = false, bool EW16 = false>
+static int launch_variant(const CUtensorMap* tm, const GemmShape& s, const EpiParams& ep, cudaStream_t stream) {
+  return launch_variant_maps<CG, BN, NS, ST, COAL, TN, EW16, false>(tm, s, ep, g_no_maps, stream);
 }
 
 struct Variant {
@@ -38,21 +44,32 @@ struct Variant {
   int (*launch_coalesced)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);   // EGOTAP_EPI=coalesced
   int (*launch_tn)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);          // D = A^T B (BN = 256 only)
   int (*launch_ew16)(const CUtensorMap*, const GemmShape&, const EpiParams&, cudaStream_t);        // row-domain epilogue on 16 warps
+  int (*launch_tepi)(const CUtensorMap*, const GemmShape&, const EpiParams&, const EpiMaps&, cudaStream_t);   // TMA epilogue (fp32 out)
 };
 
 static const Variant kVariants[] = {
-    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>, nullptr, nullptr},
-    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>, nullptr, nullptr},
+    {"cg1_bn128_bf16_s6", 1, 128, 1, &launch_variant<1, 128, 1, 6>, &launch_variant<1, 128, 1, 6, true>, nullptr, nullptr, nullptr},
+    {"cg1_bn128_bf16x3_s3", 1, 128, 3, &launch_variant<1, 128, 3, 3>, &launch_variant<1, 128, 3, 3, true>, nullptr, nullptr, nullptr},
     {"cg1_bn256_bf16_s4", 1, 256, 1, &launch_variant<1, 256, 1, 4>, &launch_variant<1, 256, 1, 4, true>,
-     &launch_variant<1, 256, 1, 4, true, true>, nullptr},
+     &launch_variant<1, 256, 1, 4, true, true>, nullptr, nullptr},
     {"cg1_bn256_bf16x3_s2", 1, 256, 3, &launch_variant<1, 256, 3, 2>, &launch_variant<1, 256, 3, 2, true>,
-     &launch_variant<1, 256, 3, 2, true, true>, nullptr},
+     &launch_variant<1, 256, 3, 2, true, true>, nullptr, nullptr},
+    // the TMA-epilogue forms trade operand-ring stages for the epilogue boxes (gemm.cuh): 4 stages + 3 boxes per warp in bf16
+    // mode, 3 stages + 1 box in the parity mode (both fill the 227 KB exactly)
     {"cg2_bn256_bf16_s6", 2, 256, 1, &launch_variant<2, 256, 1, 6>, &launch_variant<2, 256, 1, 6, true>,
-     &launch_variant<2, 256, 1, 6, true, true>, &launch_variant<2, 256, 1, 6, false, false, true>},
+     &launch_variant<2, 256, 1, 6, true, true>, &launch_variant<2, 256, 1, 6, false, false, true>,
+     &launch_variant_maps<2, 256, 1, 4, false, false, false, true>},
     {"cg2_bn256_bf16x3_s3", 2, 256, 3, &launch_variant<2, 256, 3, 3>, &launch_variant<2, 256, 3, 3, true>,
-     &launch_variant<2, 256, 3, 3, true, true>, &launch_variant<2, 256, 3, 3, false, false, true>},
+     &launch_variant<2, 256, 3, 3, true, true>, &launch_variant<2, 256, 3, 3, false, false, true>,
+     &launch_variant_maps<2, 256, 3, 3, false, false, false, true>},
 };
 static const int kNumVariants = int(sizeof(kVariants) / sizeof(kVariants[0]));
+
+// EGOTAP_EPI_TMA=0 keeps the load / store epilogue for fp32 outputs (A/B runs and tests; read per call)
+static int tepi_mode() {
+  const char* e = getenv("EGOTAP_EPI_TMA");
+  return (e && e[0] == '0') ? 0 : 1;
+}
 
 static int g_prefer_cg = -1;
 static int prefer_cg() {
@@ -148,6 +165,32 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
   if (const char* epi_env = getenv("EGOTAP_EPI")) {
     if (strcmp(epi_env, "coalesced") == 0) coalesced = true;
     else if (strcmp(epi_env, "rows") == 0) coalesced = false;
+  }
+  // Measured on the B200 (profiles/r02g_tma_epilogue.md, bf16 mode): out-projection (K = 1024) 682 -> 926 TFLOP/s, patch embedding
+  // (K = 256) 185 -> 247, but MLP-down (K = 4096, main-loop bound with the 6-stage ring) 1,359 -> 1,222 on the 4-stage ring the
+  // boxes leave room for: the TMA epilogue is used where the main loop of a tile is short (K <= 1024).
+  if (coalesced && v.launch_tepi && tepi_mode() != 0 && s.K <= 1024) {
+    // TMA epilogue (gemm.cuh, TEPI): fp32 row-major output only, and every 32-row box of a warp must map to 32 consecutive
+    // output rows and 32 consecutive residual rows
+    const bool rows_ok = s.M % 32 == 0 && (ep.rows_in == 0 || ep.rows_in % 32 == 0) && (ep.resid_mod == 0 || ep.resid_mod % 32 == 0);
+    const bool out_ok = ep.out_f32 && !ep.out_hi && !ep.out_lo && ep.store == STORE_ROWMAJOR && ep.ldo % 4 == 0 && ep.col_off % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0 && ep.col_off + s.N <= ep.ldo;
+    const bool res_ok = ep.resid == nullptr || (ep.resid_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0 &&
+                                                 ep.col_off + s.N <= ep.resid_ld);
+    if (rows_ok && out_ok && res_ok) {
+      const long long last = s.M - 1;
+      const long long out_rows = (long long)(s.groups - 1) * ep.group_rows +
+                                 (ep.rows_in > 0 ? (last / ep.rows_in) * ep.rows_out + last % ep.rows_in : last) + 1;
+      EpiMaps maps;
+      if ((rc = make_operand_tmap(&maps.out, ep.out_f32, 2 * ep.ldo, out_rows, 2 * ep.ldo, 1, 0, 1, 0, 32))) return rc;
+      if (ep.resid) {
+        const long long res_rows = ep.resid_mod > 0 ? ep.resid_mod : out_rows;
+        if ((rc = make_operand_tmap(&maps.res, ep.resid, 2 * ep.resid_ld, res_rows, 2 * ep.resid_ld, 1, 0, 1, 0, 32))) return rc;
+      } else {
+        maps.res = maps.out;
+      }
+      return v.launch_tepi(tm, sh, ep, maps, stream);
+    }
   }
   if (coalesced) return v.launch_coalesced(tm, sh, ep, stream);
   // row-domain epilogue: 16 warps for the GELU epilogue (MLP-up), where the math per element is long enough for four warps per

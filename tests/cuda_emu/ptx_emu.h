@@ -14,6 +14,9 @@
 // TMA destination holds bf16 NaN in between.  A missing wait therefore shows up as NaN / stale results, a wait that can
 // never be satisfied as a deadlock (fiber scheduler).  Proxy fences and finer memory-ordering rules are not modelled.
 #pragma once
+#include <deque>
+#include <map>
+#include <memory>
 #include "cuda_emu.h"
 
 #include <cstdio>
@@ -107,6 +110,56 @@ inline void tma_load_to(uint8_t* dst, const CUtensorMap* tm_, void* bar, int c0,
   eb_emu::defer_tma([=]() { tma_load_now(dst, &tm, bar, c0, c1, c2, c3); });
 }
 inline void tma_prefetch_4d(const CUtensorMap*, int, int, int, int) {}   // L2 prefetch: no functional effect
+// ---- TMA store + bulk async-groups.  The shared-memory source is read WHEN THE STORE EXECUTES (a later scheduler round), so a
+// box that is rewritten before cp.async.bulk.wait_group.read allowed it shows up as corrupted output.
+struct EmuBulkGroup { int outstanding = 0; };
+struct EmuBulkState { std::shared_ptr<EmuBulkGroup> open; std::deque<std::shared_ptr<EmuBulkGroup>> committed; };
+inline EmuBulkState& emu_bulk_state() {
+  static std::map<uint64_t, EmuBulkState> st;
+  return st[(uint64_t(blockIdx.x) << 32) | uint64_t(threadIdx.x)];
+}
+inline void tma_store_now(const uint8_t* src, const EmuTmap* tm, int c0, int c1, int c2, int c3) {
+  for (uint32_t r = 0; r < tm->box_rows; ++r)
+    for (uint32_t i = 0; i < 64; ++i) {
+      const uint64_t k = uint64_t(c0) + i, row = uint64_t(c1) + r;
+      if (!(c0 >= 0 && c1 >= 0 && k < tm->dims[0] && row < tm->dims[1] && uint64_t(c2) < tm->dims[2] && uint64_t(c3) < tm->dims[3])) continue;
+      uint32_t off = r * 128 + i * 2;
+      off ^= ((off >> 7) & 7) << 4;                       // 128-byte swizzle
+      memcpy(const_cast<uint8_t*>(tm->base) + k * 2 + row * tm->strides[0] + uint64_t(c2) * tm->strides[1] + uint64_t(c3) * tm->strides[2],
+             src + off, 2);
+    }
+}
+inline void tma_store_4d(const CUtensorMap* tm_, const void* src_, int c0, int c1, int c2, int c3) {
+  const EmuTmap tm = *reinterpret_cast<const EmuTmap*>(tm_);
+  if (tm.magic != 0x7e4a0001u) { fprintf(stderr, "ptx_emu: not an emulated tensor map\n"); abort(); }
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(src_);
+  if (uint32_t(src - eb_emu::dyn_smem()) % 1024) { fprintf(stderr, "ptx_emu: TMA source must be 1024-byte aligned for the 128B swizzle\n"); abort(); }
+  EmuBulkState& st = emu_bulk_state();
+  if (!st.open) st.open = std::make_shared<EmuBulkGroup>();
+  std::shared_ptr<EmuBulkGroup> grp = st.open;
+  ++grp->outstanding;
+  eb_emu::defer_tma([=]() { tma_store_now(src, &tm, c0, c1, c2, c3); --grp->outstanding; });
+}
+inline void bulk_commit() {
+  EmuBulkState& st = emu_bulk_state();
+  if (!st.open) st.open = std::make_shared<EmuBulkGroup>();
+  st.committed.push_back(st.open);
+  st.open.reset();
+}
+template <int N>
+inline void bulk_wait_read() {
+  EmuBulkState& st = emu_bulk_state();
+  for (;;) {
+    while (!st.committed.empty() && st.committed.front()->outstanding == 0) st.committed.pop_front();
+    int pending = 0;
+    for (auto& g : st.committed) pending += g->outstanding > 0 ? 1 : 0;
+    // groups complete in order in this model: "at most N pending" = at most N committed groups left
+    if (int(st.committed.size()) <= N || pending == 0) return;
+    eb_emu::yield_wait();
+  }
+}
+template <int N>
+inline void bulk_wait() { bulk_wait_read<N>(); }
 inline void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   tma_load_to(reinterpret_cast<uint8_t*>(dst), tm, bar, c0, c1, c2, c3);
 }
@@ -269,7 +322,6 @@ inline void tmem_st_n(uint32_t taddr, const uint32_t* r, int n) {
 inline void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_n(taddr, r, 32); }
 inline void tmem_st16(uint32_t taddr, const uint32_t* r) { tmem_st_n(taddr, r, 16); }
 inline void tmem_st_wait() {}
-inline void l2_prefetch_bulk(const void*, uint32_t) {}
 template <int N> inline void warpgroup_reg_dec() {}
 template <int N> inline void warpgroup_reg_inc() {}
 inline int pin_reg(int v) { return v; }

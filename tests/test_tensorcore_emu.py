@@ -121,6 +121,68 @@ def test_gemm_epilogue_modes(be, variant, prec):
     _close(e1["out_f32"], e2["out_f32"], tol)
 
 
+@pytest.mark.parametrize("variant,prec", [(4, 1), (5, 0)])
+def test_tma_epilogue(be, variant, prec):
+    """the TMA epilogue of the paired-SM GEMMs (gemm.cuh TEPI: residual boxes by TMA a few chunks ahead across tile boundaries,
+    rows added in place in the swizzled box, TMA store; 3 boxes per warp in bf16 mode, 1 in the parity mode) against the oracle
+    and bit for bit against the load / store epilogue it replaces (EGOTAP_EPI_TMA=0); also with late TMA loads"""
+    import ctypes as C
+    emu, _ = be
+    lib = _emu_lib()
+    lib.emu_set_tma_latency.argtypes = [C.c_int, C.c_ulonglong]
+    tol = 2e-5 if prec == 0 else 1e-6
+    torch.manual_seed(70 + variant)
+    N, K = 768, 128                       # 3 column tiles; with M = 640: 3 row tiles, the last one half outside the matrix
+    b, bias = torch.randn(N, K), torch.randn(N)
+
+    def run_cases():
+        torch.manual_seed(700 + variant)      # the same inputs in every pass
+        outs = []
+        # in-place residual stream (the output projection / MLP-down), several tiles per persistent cluster
+        M = 640
+        a, h0 = torch.randn(M, K), torch.randn(M, N)
+        hs = [h0.clone(), h0.clone()]
+        it = iter(hs)
+
+        def inplace():
+            h = next(it)
+            return dict(bias=bias, resid=h, resid_ld=N, out_f32=h, ldo=N)
+        _run_both(be, a, b, M, N, K, prec, variant, inplace)
+        _close(hs[0], hs[1], tol)
+        outs.append(hs[0])
+        # additive table + row re-layout (the patch embedding), output narrower than its buffer (col_off, ldo > N)
+        live, tok, B = 96, 128, 4
+        a = torch.randn(B * live, K)
+        table = torch.randn(live, N + 64)                 # the column offset applies to the table as well
+        e1, e2 = _run_both(be, a, b, B * live, N, K, prec, variant,
+                           lambda: dict(resid=table, resid_ld=N + 64, resid_mod=live, rows_in=live, rows_out=tok, col_off=32,
+                                        out_f32=torch.full((B * tok, N + 64), float("nan")), ldo=N + 64))
+        _close(e1["out_f32"], e2["out_f32"], tol)
+        outs.append(e1["out_f32"])
+        # no residual, scale + LeakyReLU, groups with fewer rows than a tile (fp32 partial products of the split-K FC block)
+        G, Mg = 3, 96
+        a, b3 = torch.randn(G * Mg, K), torch.randn(G * N, K)
+        scale = torch.rand(N) + 0.5
+        e1, e2 = _run_both(be, a, b3, Mg, N, K, prec, variant,
+                           lambda: dict(scale=scale, bias=bias, act=2, group_rows=Mg, out_f32=torch.full((G * Mg, N), float("nan")), ldo=N),
+                           groups=G, a_group=(G, Mg * K, 1, 0), b_group=(G, N * K, 1, 0), a_rows=Mg, b_rows=N)
+        _close(e1["out_f32"], e2["out_f32"], tol)
+        outs.append(e1["out_f32"])
+        return outs
+    try:
+        tma = run_cases()
+        with _env("EGOTAP_EPI_TMA", "0"):
+            ldst = run_cases()
+        for x, y in zip(tma, ldst):
+            assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+        lib.emu_set_tma_latency(9, 5)
+        late = run_cases()
+        for x, y in zip(tma, late):
+            assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+    finally:
+        lib.emu_set_tma_latency(0, 0)
+
+
 class _env:
     """set / unset one environment switch for the duration of a block (the library reads these two per call)"""
 
