@@ -222,6 +222,72 @@ def test_fused_attention_backward_matches_autograd(case):
         assert ((got - ref).abs().max() / ref.abs().max()).item() < 4e-2, name
 
 
+@pytest.mark.parametrize("x3", [True, False])
+def test_tma_epilogue_equals_the_load_store_epilogue(x3, monkeypatch):
+    """fp32-output GEMMs with a short main loop go through the TMA epilogue (gemm.cuh TEPI: residual boxes by TMA ahead of use,
+    rows added in place, TMA store).  The same calls with EGOTAP_EPI_TMA=0 use the load / store epilogue: the results must be
+    bit-identical (same arithmetic per element), also in place on the residual stream and over many tiles per persistent cluster;
+    both against fp64.  Shapes of the lifting path: out-projection, patch embedding (additive table, 480 -> 576 row re-layout),
+    last-layer projection over the live tokens of every frame (groups with a tile-ragged row count)."""
+    from egotap_b200 import capi
+    torch.manual_seed(12)
+    prec = capi.PREC_BF16X3 if x3 else capi.PREC_BF16
+    tol = 3e-5 if x3 else 1e-5
+
+    def both(run):
+        monkeypatch.delenv("EGOTAP_EPI_TMA", raising=False)
+        a = run()
+        monkeypatch.setenv("EGOTAP_EPI_TMA", "0")
+        b = run()
+        monkeypatch.delenv("EGOTAP_EPI_TMA", raising=False)
+        assert torch.isnan(a).equal(torch.isnan(b)) and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))   # NaN = never written
+        return a
+
+    # out-projection: in place on the residual stream, 96 x 4 tiles over 74 clusters
+    M, N, K = 96 * 256, 1024, 1024
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.05
+    ah, al, bh, bl, Ar, Br = _ops(A, B, x3)
+    bias, h0 = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+
+    def outproj():
+        h = h0.clone()
+        capi.gemm(ah, al, bh, bl, M, N, K, precision=prec, bias=bias, resid=h, resid_ld=N, out_f32=h)
+        return h
+    got = both(outproj)
+    ref = Ar @ Br.t() + bias.double() + h0.double()
+    assert ((got.double() - ref).abs().max() / ref.abs().max()).item() < tol
+    # patch embedding: additive table indexed by the row inside the frame, rows re-laid out 480 -> 576 per frame
+    frames, live, tok, K2 = 40, 480, 576, 256
+    A2, B2 = torch.randn(frames * live, K2, device="cuda"), torch.randn(N, K2, device="cuda") * 0.1
+    a2h, a2l, b2h, b2l, A2r, B2r = _ops(A2, B2, x3)
+    table = torch.randn(live, N, device="cuda")
+
+    def patch():
+        out = torch.full((frames * tok, N), float("nan"), device="cuda")
+        capi.gemm(a2h, a2l, b2h, b2l, frames * live, N, K2, precision=prec, resid=table, resid_ld=N, resid_mod=live, rows_in=live,
+                  rows_out=tok, out_f32=out)
+        return out
+    got = both(patch).view(frames, tok, N)
+    ref = (A2r @ B2r.t()).view(frames, live, N) + table.double()
+    assert ((got[:, :live].double() - ref).abs().max() / ref.abs().max()).item() < tol
+    assert torch.isnan(got[:, live:]).all()                  # the rows of the dummy tokens are not touched
+    # groups of 480 rows (two 256-row tiles, the second half outside) sharing one weight matrix, in place
+    G = 24
+    A3 = torch.randn(G * tok, K, device="cuda")
+    a3h, a3l, b3h, b3l, A3r, _ = _ops(A3, B.repeat(G, 1), x3)       # one copy of the weight matrix per group
+    g0 = torch.randn(G * tok, N, device="cuda")
+
+    def grouped():
+        h = g0.clone()
+        capi.gemm(a3h, a3l, b3h, b3l, live, N, K, precision=prec, groups=G, a_group=(G, tok * K, 1, 0), b_group=(G, N * K, 1, 0),
+                  a_rows=live, b_rows=N, bias=bias, resid=h, resid_ld=N, out_f32=h, group_rows=tok)
+        return h
+    got = both(grouped).view(G, tok, N)
+    ref = (A3r.view(G, tok, K)[:, :live] @ Br.t()) + bias.double() + g0.view(G, tok, N)[:, :live].double()
+    assert ((got[:, :live].double() - ref).abs().max() / ref.abs().max()).item() < tol
+    assert torch.equal(got[:, live:], g0.view(G, tok, N)[:, live:])
+
+
 def test_argument_errors_are_reported_not_fatal():
     from egotap_b200 import capi
     A = torch.zeros(128, 96, device="cuda", dtype=torch.bfloat16)
