@@ -46,6 +46,16 @@ struct EpiParams {
   int J;
   // STORE_HEAD_MERGE: group g = frame*heads + h  ->  out row = frame*tokens + m, column += h*N
   int heads;
+  // LayerNorm folded into the GEMMs around it (plan.cu, "LayerNorm fold"):
+  //  * producer (the GEMM that writes the residual stream): stats_out[out_row * stats_parts + c / 128] = (sum, sum of squares) of
+  //    the values it stores in columns [128 (c / 128), +128) of that row -- one entry per epilogue warp and tile
+  //  * consumer (the GEMM whose A operand is the un-normalised row, its weights pre-multiplied by gamma):
+  //    v = (acc * alpha - mean_r * scale[n]) * rstd_r + bias[n], mean / rstd from stats_in[out_row * stats_parts + 0 .. parts)
+  //    over ln_cols columns (scale[n] = sum_k gamma_k W[n][k], bias[n] = b[n] + sum_k beta_k W[n][k])
+  float2* stats_out;
+  const float2* stats_in;
+  int stats_parts, ln_cols;
+  float ln_eps;
 };
 
 // Tensor maps of the TMA epilogue (TEPI): the fp32 output and the fp32 residual / additive table, described as bf16 matrices
@@ -114,7 +124,38 @@ __device__ __forceinline__ bool epi_wide_ok(const EpiParams& p) {
 // shared memory by the epilogue threads (one column each, requested BEFORE the accumulator wait) and read back as warp-wide
 // broadcasts: the first version fetched them with __ldg inside the chunk loop, and the first use of every chunk sat on that
 // L2 round trip (ncu, bf16 mode: 13-17 % of all samples of the QKV / MLP-up GEMMs on the first bias FADD of a chunk).
-__device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* sv_scale, const float* sv_bias, float (&v)[32]) {
+struct EpiLn {             // per-thread (= per-row) LayerNorm statistics of the consumer form; rstd == 0: not folded
+  float mean, rstd;
+};
+__device__ __forceinline__ EpiLn epi_ln_row(const EpiParams& p, long long orow, bool row_ok) {
+  EpiLn ln{0.f, 0.f};
+  if (p.stats_in != nullptr && row_ok) {
+    const float2* st = p.stats_in + orow * p.stats_parts;
+    float sum = 0.f, sq = 0.f;
+    for (int i = 0; i < p.stats_parts; ++i) { const float2 t = __ldg(st + i); sum += t.x; sq += t.y; }
+    const float inv_n = 1.0f / float(p.ln_cols);
+    ln.mean = sum * inv_n;
+    const float var = fmaxf(sq * inv_n - ln.mean * ln.mean, 0.f);
+    ln.rstd = 1.0f / sqrtf(var + p.ln_eps);
+  }
+  return ln;
+}
+__device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* sv_scale, const float* sv_bias, float (&v)[32],
+                                               const EpiLn ln = EpiLn{0.f, 0.f}) {
+  if (p.stats_in != nullptr) {     // LayerNorm fold: (acc - mean * s[n]) * rstd + c[n]
+    const float4* s4 = reinterpret_cast<const float4*>(sv_scale);
+    const float4* b4 = reinterpret_cast<const float4*>(sv_bias);
+    const float nm = -ln.mean;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s = s4[j], b = b4[j];
+      v[4 * j] = fmaf(fmaf(nm, s.x, v[4 * j]), ln.rstd, b.x);
+      v[4 * j + 1] = fmaf(fmaf(nm, s.y, v[4 * j + 1]), ln.rstd, b.y);
+      v[4 * j + 2] = fmaf(fmaf(nm, s.z, v[4 * j + 2]), ln.rstd, b.z);
+      v[4 * j + 3] = fmaf(fmaf(nm, s.w, v[4 * j + 3]), ln.rstd, b.w);
+    }
+    return;
+  }
   if (p.scale) {
     const float4* s4 = reinterpret_cast<const float4*>(sv_scale);
 #pragma unroll
@@ -135,11 +176,12 @@ __device__ __forceinline__ void epi_scale_bias(const EpiParams& p, const float* 
 
 template <bool RESID = true>
 __device__ __forceinline__ void epi_apply(const EpiParams& p, const EpiRow& row, int m, int n0, int N, uint32_t (&r)[32],
-                                          const float4 (&t)[8], const float* sv_scale, const float* sv_bias, bool wide) {
+                                          const float4 (&t)[8], const float* sv_scale, const float* sv_bias, bool wide,
+                                          const EpiLn ln = EpiLn{0.f, 0.f}) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-  epi_scale_bias(p, sv_scale, sv_bias, v);
+  epi_scale_bias(p, sv_scale, sv_bias, v, ln);
   if (p.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -256,11 +298,12 @@ __device__ __forceinline__ void epi_load_resid_t(const EpiParams& p, const EpiRo
 }
 __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const EpiRow& row, const EpiRowsT& rows, int n0,
                                                     uint32_t (&r)[32], const float4 (&t)[8], float4* stg, int lane,
-                                                    const float* sv_scale, const float* sv_bias) {
+                                                    const float* sv_scale, const float* sv_bias, const EpiLn ln,
+                                                    float (&st_sum)[8], float (&st_sq)[8]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-  epi_scale_bias(p, sv_scale, sv_bias, v);
+  epi_scale_bias(p, sv_scale, sv_bias, v, ln);
   if (p.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -280,6 +323,10 @@ __device__ __forceinline__ void epi_apply_coalesced(const EpiParams& p, const Ep
     epi_row_extras(p, row, rows.orow[i], rr, rrow_unused, cs);
     if ((rows.ok >> i) & 1u) {
       if (p.resid) { x.x += t[i].x; x.y += t[i].y; x.z += t[i].z; x.w += t[i].w; }
+      if (p.stats_out) {           // this lane's 4 columns of row 4 i + sub; the 8 lanes of the row are summed at the end of the tile
+        st_sum[i] += (x.x + x.y) + (x.z + x.w);
+        st_sq[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+      }
       const long long o = (long long)rows.orow[i] * p.ldo + n0 + p.col_off + cs + seg * 4;
       if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
       if (p.out_hi) {
@@ -545,6 +592,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         int g, m0, n_first;
         const int nc = tile_boxes(tile, g, m0, n_first);
         const EpiRow row0 = epi_row(ep, g, m0 < s.M ? m0 : 0, s.N);
+        const long long orow_lane = row0.orow + lane;            // boxes map to 32 consecutive output rows (eligibility)
+        const EpiLn ln = epi_ln_row(ep, orow_lane, nc > 0);
+        float st_sum = 0.f, st_sq = 0.f;                         // LayerNorm-fold producer: this row over the warp's columns
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
 #pragma unroll 1
         for (int c = 0; c < nc; ++c, ++n) {
@@ -561,7 +611,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-          epi_scale_bias(ep, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, v);
+          epi_scale_bias(ep, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, v, ln);
           if (ep.act == ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -583,6 +633,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             float4* pp = rowp + (j ^ (lane & 7));           // 128-byte swizzle: 16-byte piece j of row r sits at piece j ^ (r & 7)
             if (has_resid) { const float4 t = *pp; x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w; }
             *pp = x;
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+          }
+          if (ep.stats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { st_sum += v[j]; st_sq = fmaf(v[j], v[j], st_sq); }
+          }
+          if (ep.out_hi != nullptr) {             // the stored row also as a bf16 (hi / lo) operand: 64 bytes per thread and part
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_pack2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
+            const long long o = orow_lane * ep.ldo + n0 + ep.col_off;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              st_global_256(ep.out_hi + o + 16 * e, hh[8 * e], hh[8 * e + 1], hh[8 * e + 2], hh[8 * e + 3], hh[8 * e + 4], hh[8 * e + 5],
+                            hh[8 * e + 6], hh[8 * e + 7]);
+            if (ep.out_lo != nullptr) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                st_global_256(ep.out_lo + o + 16 * e, ll[8 * e], ll[8 * e + 1], ll[8 * e + 2], ll[8 * e + 3], ll[8 * e + 4], ll[8 * e + 5],
+                              ll[8 * e + 6], ll[8 * e + 7]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -591,6 +662,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             bulk_commit();
           }
         }
+        if (ep.stats_out != nullptr && nc > 0) ep.stats_out[orow_lane * ep.stats_parts + n_first / 128] = make_float2(st_sum, st_sq);
         if (nc == 0) {                          // a warp whose rows / columns lie outside the matrix still hands the buffer back
           tc_fence_before();
           __syncwarp();
@@ -624,6 +696,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       const bool row_ok = m < s.M;
       const bool use_resid = ep.resid != nullptr && row_ok;
       const EpiRow row = epi_row(ep, g, row_ok ? m : 0, s.N);
+      const EpiLn ln = epi_ln_row(ep, row.orow, row_ok);
       float4 t_cur[8], t_nxt[8];
       const int n_first = n_blk * BN + col_base;
       if constexpr (COAL) {
@@ -634,6 +707,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         // uses them, 22 % of the out-projection's samples sat on the first residual FADD of a chunk)
         const bool has_resid = ep.resid != nullptr && ep.store != STORE_QKV;
         if (has_resid && n_first < s.N) epi_load_resid_t(ep, row, rows, n_first, lane, t_cur);
+        float st_sum[8], st_sq[8];                 // LayerNorm-fold producer: row sums of this warp's columns (transposed domain)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { st_sum[i] = 0.f; st_sq[i] = 0.f; }
 #pragma unroll 1
         for (int c = 0; c < C::COLS_PER_EPI_GROUP / 32; ++c) {
           const int n0 = n_first + c * 32;
@@ -647,13 +723,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           const float* svs = sv_scale + col_base + c * 32;
           const float* svb = sv_bias + col_base + c * 32;
           if (v_part) {
-            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, svs, svb, wide);
+            if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, svs, svb, wide, ln);
           } else {
-            epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane, svs, svb);
+            epi_apply_coalesced(ep, row, rows, n0, r, t_cur, stg, lane, svs, svb, ln, st_sum, st_sq);
           }
           if (has_resid && more) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];
+          }
+        }
+        if (ep.stats_out != nullptr && n_first < s.N) {
+          // the 8 lanes that hold the 16-byte pieces of a row (same lane / 8) add up; piece 0's lane writes the entry of the
+          // warp's 128-column part
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+              st_sum[i] += __shfl_xor_sync(0xffffffffu, st_sum[i], d);
+              st_sq[i] += __shfl_xor_sync(0xffffffffu, st_sq[i], d);
+            }
+            if ((lane & 7) == 0 && ((rows.ok >> i) & 1u))
+              ep.stats_out[(long long)rows.orow[i] * ep.stats_parts + n_first / 128] = make_float2(st_sum[i], st_sq[i]);
           }
         }
         tc_fence_before();
@@ -672,7 +762,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           uint32_t r[32];
           tmem_ld32(t_addr + col_base + c * 32, r);
           tmem_ld_wait();
-          if (row_ok) epi_apply<false>(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide);
+          if (row_ok) epi_apply<false>(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide, ln);
         }
       } else {
       if (use_resid && n_first < s.N) epi_load_resid(ep, row, n_first, t_cur, wide);
@@ -685,7 +775,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const bool more = (c + 1 < C::COLS_PER_EPI_GROUP / 32) && (n0 + 32 < s.N);
         if (use_resid && more) epi_load_resid(ep, row, n0 + 32, t_nxt, wide);   // prefetch the next chunk's residual
         tmem_ld_wait();
-        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide);
+        if (row_ok) epi_apply(ep, row, m, n0, s.N, r, t_cur, sv_scale + col_base + c * 32, sv_bias + col_base + c * 32, wide, ln);
         if (use_resid && more) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) t_cur[j] = t_nxt[j];

@@ -166,6 +166,7 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
     if (strcmp(epi_env, "coalesced") == 0) coalesced = true;
     else if (strcmp(epi_env, "rows") == 0) coalesced = false;
   }
+  if (ep.stats_out != nullptr) coalesced = true;      // the LayerNorm-fold producers: row statistics exist in these two forms only
   // Measured on the B200 (profiles/r02g_tma_epilogue.md, bf16 mode): out-projection (K = 1024) 682 -> 926 TFLOP/s, patch embedding
   // (K = 256) 185 -> 247, but MLP-down (K = 4096, main-loop bound with the 6-stage ring) 1,359 -> 1,222 on the 4-stage ring the
   // boxes leave room for: the TMA epilogue is used where the main loop of a tile is short (K <= 1024).
@@ -173,7 +174,11 @@ int gemm_run(const GemmOperand& a, const GemmOperand& b, const GemmShape& s, con
     // TMA epilogue (gemm.cuh, TEPI): fp32 row-major output only, and every 32-row box of a warp must map to 32 consecutive
     // output rows and 32 consecutive residual rows
     const bool rows_ok = s.M % 32 == 0 && (ep.rows_in == 0 || ep.rows_in % 32 == 0) && (ep.resid_mod == 0 || ep.resid_mod % 32 == 0);
-    const bool out_ok = ep.out_f32 && !ep.out_hi && !ep.out_lo && ep.store == STORE_ROWMAJOR && ep.ldo % 4 == 0 && ep.col_off % 4 == 0 &&
+    // (a bf16 copy of the stored rows -- the LayerNorm-fold producers -- is written with 32-byte row-domain stores)
+    const bool bf_ok = (!ep.out_hi && !ep.out_lo) ||
+                       (ep.out_hi && ep.ldo % 16 == 0 && ep.col_off % 16 == 0 &&
+                        ((reinterpret_cast<uintptr_t>(ep.out_hi) | reinterpret_cast<uintptr_t>(ep.out_lo)) & 31) == 0);
+    const bool out_ok = ep.out_f32 && bf_ok && ep.store == STORE_ROWMAJOR && ep.ldo % 4 == 0 && ep.col_off % 4 == 0 &&
                         (reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0 && ep.col_off + s.N <= ep.ldo;
     const bool res_ok = ep.resid == nullptr || (ep.resid_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0 &&
                                                  ep.col_off + s.N <= ep.resid_ld);
@@ -221,6 +226,7 @@ extern "C" int egotap_b200_gemm(const egotap_gemm* d, void* stream) {
   GemmShape s{d->M, d->N, d->K, d->groups, 0, 0};
   const egotap_epilogue& e = d->epi;
   EpiParams ep;
+  memset(&ep, 0, sizeof(ep));       // the LayerNorm-fold fields are internal to the lifting plan
   ep.alpha = e.alpha; ep.scale = e.scale; ep.bias = e.bias; ep.act = e.act;
   ep.resid = e.resid; ep.resid_ld = e.resid_ld; ep.resid_mod = e.resid_mod;
   ep.rows_in = e.rows_in; ep.rows_out = e.rows_out; ep.group_rows = e.group_rows;

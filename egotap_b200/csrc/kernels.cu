@@ -114,18 +114,78 @@ int ingest_run(const float* x, int B, int J, __nv_bfloat16* p_hi, __nv_bfloat16*
 // precomputed at pack time; reference model/modeling_vit.py:137-153)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fill_dummy_kernel(float4* __restrict__ hidden, const float4* __restrict__ dummy,
-                                                         int tokens, int live) {
+                                                         int tokens, int live, __nv_bfloat16* __restrict__ xb_hi,
+                                                         __nv_bfloat16* __restrict__ xb_lo, float2* __restrict__ stats) {
   const int nd = tokens - live;
   const long long b = blockIdx.x / nd;
   const int i = blockIdx.x % nd;
-  hidden[(b * tokens + live + i) * 256 + threadIdx.x] = __ldg(dummy + i * 256 + threadIdx.x);
+  const long long row = b * tokens + live + i;
+  const float4 v = __ldg(dummy + i * 256 + threadIdx.x);
+  hidden[row * 256 + threadIdx.x] = v;
+  if (xb_hi != nullptr) {            // LayerNorm fold (plan.cu): the row also as the bf16 operand + its (sum, sum of squares) per 128 columns
+    store_split4(xb_hi, xb_lo, row * 1024 + threadIdx.x * 4, v);
+    const float s = warp_sum((v.x + v.y) + (v.z + v.w));
+    const float q = warp_sum(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+    if ((threadIdx.x & 31) == 0) stats[row * 8 + (threadIdx.x >> 5)] = make_float2(s, q);     // warp w holds columns [128 w, +128)
+  }
 }
 
-int fill_dummy_run(float* hidden, const float* dummy, int B, int tokens, int live, cudaStream_t stream) {
+int fill_dummy_run(float* hidden, const float* dummy, int B, int tokens, int live, cudaStream_t stream, __nv_bfloat16* xb_hi,
+                   __nv_bfloat16* xb_lo, float2* stats) {
   if (tokens == live) return 0;
   ProfScope prof("fill_dummy_kernel", stream);
-  EB_LAUNCH(fill_dummy_kernel, B * (tokens - live), 256, stream, (float4*)hidden, (const float4*)dummy, tokens, live);
+  EB_LAUNCH_COOP(fill_dummy_kernel, B * (tokens - live), 256, stream, (float4*)hidden, (const float4*)dummy, tokens, live, xb_hi, xb_lo, stats);
   EB_CHECK_LAUNCH("fill_dummy_kernel");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm fold, weight packing (plan.cu): W'[n][k] = W[n][k] gamma[k] as bf16 hi(/lo);
+//   s[n] = sum_k W'[n][k] (of the ROUNDED operand the tensor cores will see, so that mean * s[n] cancels exactly what the GEMM
+//   accumulated), c[n] = b[n] + sum_k beta[k] W[n][k].   K = 1024, one CTA per output row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_fold_pack_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           float* __restrict__ s_out, float* __restrict__ c_out) {
+  __shared__ double red[2][8];
+  const long long n = blockIdx.x;
+  const int k = threadIdx.x * 4;
+  const float4 w = __ldg(reinterpret_cast<const float4*>(W + n * 1024 + k));
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + k));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beta + k));
+  const float4 wp = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+  store_split4(hi, lo, n * 1024 + k, wp);
+  const float e[4] = {wp.x, wp.y, wp.z, wp.w};
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat16 h, l;
+    split_bf16(e[j], h, l);
+    s += double(__bfloat162float(h)) + (lo != nullptr ? double(__bfloat162float(l)) : 0.0);
+  }
+  double c = double(w.x) * b.x + double(w.y) * b.y + double(w.z) * b.z + double(w.w) * b.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0.0, cc = 0.0;
+    for (int i = 0; i < 8; ++i) { ss += red[0][i]; cc += red[1][i]; }
+    s_out[n] = float(ss);
+    c_out[n] = float(cc + double(__ldg(bias + n)));
+  }
+}
+
+int ln_fold_pack_run(const float* W, const float* bias, const float* gamma, const float* beta, int N, __nv_bfloat16* hi,
+                     __nv_bfloat16* lo, float* s_out, float* c_out, cudaStream_t stream) {
+  EB_REQUIRE(W && bias && gamma && beta && hi && s_out && c_out && N > 0, "ln_fold_pack: bad arguments");
+  ProfScope prof("ln_fold_pack_kernel", stream);
+  EB_LAUNCH_COOP(ln_fold_pack_kernel, N, 256, stream, W, bias, gamma, beta, hi, lo, s_out, c_out);
+  EB_CHECK_LAUNCH("ln_fold_pack_kernel");
   return 0;
 }
 

@@ -14,7 +14,8 @@ namespace eb {
 // kernels.cu
 int split2d_run(const float*, long long, long long, long long, __nv_bfloat16*, __nv_bfloat16*, long long, cudaStream_t);
 int ingest_run(const float*, int, int, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
-int fill_dummy_run(float*, const float*, int, int, int, cudaStream_t);
+int fill_dummy_run(float*, const float*, int, int, int, cudaStream_t, __nv_bfloat16* = nullptr, __nv_bfloat16* = nullptr, float2* = nullptr);
+int ln_fold_pack_run(const float*, const float*, const float*, const float*, int, __nv_bfloat16*, __nv_bfloat16*, float*, float*, cudaStream_t);
 int layernorm_run(const float*, const float*, const float*, long long, int, int, float, __nv_bfloat16*, __nv_bfloat16*,
                   float*, cudaStream_t);
 int softmax_run(const float*, long long, int, __nv_bfloat16*, __nv_bfloat16*, cudaStream_t);
@@ -37,6 +38,7 @@ constexpr int NLAYERS = 3;
 
 static bool fused_attention();
 static bool small_batch_splitk();
+static bool layernorm_fold();
 constexpr int SPLITK_MAX_FRAMES = 32, SPLITK_MAX_G = 8;
 
 struct W2 {  // bf16 hi/lo weight matrix [N][K]
@@ -100,7 +102,7 @@ static std::vector<std::string> param_names(int preset) {
 struct Plan {
   int preset, precision, nsplit, max_batch;
   int J, n_hm, grid, live, nj;
-  bool global_head, packed_ok = false, fused_attention_layout = true, splitk_layout = false;
+  bool global_head, packed_ok = false, fused_attention_layout = true, splitk_layout = false, ln_fold = false;
   std::vector<std::string> names;
   // ---- packed weights
   W2 w_patch;
@@ -108,6 +110,7 @@ struct Plan {
   struct Layer {
     W2 qkv, o, up, down;
     float *b_qkv, *b_o, *b_up, *b_down, *ln1w, *ln1b, *ln2w, *ln2b;
+    float *s_qkv, *c_qkv, *s_up, *c_up;     // LayerNorm fold: row sums of the gamma-scaled weights, bias + beta . W
   } L[NLAYERS];
   float *lnfw, *lnfb;
   struct FC {
@@ -122,6 +125,7 @@ struct Plan {
   // ---- workspace
   W2 a_patch, a_limb, ln, qk, vt, P, ctx, mlp, fin, f1, f2, xb, hg, h0b;
   float *hidden, *S, *E, *F0, *G0, *gates, *cst, *H0, *FG1, *skel, *skp = nullptr, *sky = nullptr;
+  float2* stats;                            // LayerNorm fold: (sum, sum of squares) per token row and 128-column part
   unsigned int* counters;
   size_t workspace_bytes;
 
@@ -149,6 +153,8 @@ struct Plan {
       l.b_down = p.take<float>(HID);
       l.ln1w = p.take<float>(HID); l.ln1b = p.take<float>(HID);
       l.ln2w = p.take<float>(HID); l.ln2b = p.take<float>(HID);
+      l.s_qkv = p.take<float>(3 * HID); l.c_qkv = p.take<float>(3 * HID);
+      l.s_up = p.take<float>(MLP); l.c_up = p.take<float>(MLP);
     }
     lnfw = p.take<float>(HID); lnfb = p.take<float>(HID);
     const int dims[3][2] = {{2048, 0}, {512, 2048}, {EMB, 512}};
@@ -181,6 +187,7 @@ struct Plan {
     a_limb = take2(w, B * n_hm * 8192);
     hidden = w.take<float>(B * TOK * HID);
     ln = take2(w, B * TOK * HID);
+    stats = w.take<float2>(B * TOK * (HID / 128));
     qk = take2(w, B * TOK * 2 * HID);
     vt = take2(w, B * TOK * HID);
     if (!fused_attention_layout) {  // score / probability scratch of the unfused A/B path only
@@ -233,7 +240,28 @@ static int plan_init(Plan& pl, int preset, int precision, int max_batch) {
   pl.names = param_names(preset);
   pl.fused_attention_layout = fused_attention();
   pl.splitk_layout = small_batch_splitk();
+  pl.ln_fold = layernorm_fold();
   return 0;
+}
+
+// LayerNorm fold (opt-in: EGOTAP_LN=fold; the default keeps the six in-layer LayerNorm passes).  LN(x) W^T + b =
+// rstd (x (gamma o W)^T - mean s) + c with s[n] = sum_k gamma_k W[n][k], c[n] = b[n] + sum_k beta_k W[n][k]: the GEMM that
+// writes the residual stream (patch embedding, out-projection, MLP-down) also stores the row as the bf16 (hi / lo) operand and
+// its (sum, sum of squares) per 128 columns; the GEMM that consumed the LayerNorm output (QKV, MLP-up) multiplies the
+// un-normalised row with the gamma-scaled weights and applies mean / rstd per row in its epilogue.  Operand precision is
+// unchanged (the row is split exactly as the normalised row was; the mean term is removed with the row sums of the ROUNDED
+// weights): measured on the B200, pose error vs the oracle 8.4e-5 folded vs 8.6e-5 (parity mode), ViT stages 1.8-2.0e-5 both.
+// Why it is not the default (profiles/r02i_layernorm_fold.md): it removes 1.1 ms of HBM-roofline kernels from a 31 ms step
+// (the sum of the kernel times drops 29.6 -> 28.2 ms) and the STEP does not get faster (31.4 vs 31.3 ms, three interleaved
+// pairs; bf16 mode 13.43 vs 13.54): the step runs against the 1000 W cap, the LayerNorm passes are its low-power phases, and
+// without them the clock governor settles lower (1.33 -> 1.29 GHz).  Energy per frame, not kernel time, bounds this step.
+static bool layernorm_fold() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EGOTAP_LN");
+    v = (e && std::string(e) == "fold") ? 1 : 0;
+  }
+  return v == 1;
 }
 
 // EGOTAP_ATTN=unfused selects the three-kernel attention (score GEMM, softmax, context GEMM) kept for A/B checks
@@ -307,6 +335,17 @@ static int linear_live(const Plan& pl, const W2& a, long long lda, int B, int li
   return gemm_run(A, Wt, s, e, pl.nsplit, -1, st);
 }
 
+// LayerNorm fold (layernorm_fold() above): the producer also stores the bf16 operand and the row statistics, the consumer
+// applies them
+static void produce_ln_operand(const Plan& pl, EpiParams& e) {
+  e.out_hi = pl.ln.hi; e.out_lo = pl.ln.lo;
+  e.stats_out = pl.stats; e.stats_parts = HID / 128;
+}
+static void consume_ln_operand(const Plan& pl, EpiParams& e, const float* s, const float* c) {
+  e.scale = s; e.bias = c;
+  e.stats_in = pl.stats; e.stats_parts = HID / 128; e.ln_cols = HID; e.ln_eps = 1e-12f;
+}
+
 static int pack(Plan& pl, const float* const* P, int n, cudaStream_t st) {
   EB_REQUIRE(n == int(pl.names.size()), "pack_weights: expected %d parameter pointers, got %d", int(pl.names.size()), n);
   for (int i = 0; i < n; ++i) EB_REQUIRE(P[i] != nullptr, "pack_weights: parameter %d (%s) is null", i, pl.names[i].c_str());
@@ -319,14 +358,22 @@ static int pack(Plan& pl, const float* const* P, int n, cudaStream_t st) {
   RC(split2d_run(P[i++], HID, 256, 256, pl.w_patch.hi, pl.w_patch.lo, 256, st));
   COPYF(pl.b_patch, P[i++], HID);
   for (auto& l : pl.L) {
+    // canonical order inside a layer: q, k, v, attention-output, MLP-up, MLP-down (weight, bias each), then the two LayerNorms
+    const float* const* lp = P + i;
+    const float *ln1w = lp[12], *ln1b = lp[13], *ln2w = lp[14], *ln2b = lp[15];
     for (int q = 0; q < 3; ++q) {  // query, key, value stacked along N
-      RC(split2d_run(P[i++], HID, HID, HID, l.qkv.hi + size_t(q) * HID * HID,
-                     l.qkv.lo ? l.qkv.lo + size_t(q) * HID * HID : nullptr, HID, st));
-      COPYF(l.b_qkv + q * HID, P[i++], HID);
+      __nv_bfloat16* hi = l.qkv.hi + size_t(q) * HID * HID;
+      __nv_bfloat16* lo = l.qkv.lo ? l.qkv.lo + size_t(q) * HID * HID : nullptr;
+      if (pl.ln_fold) RC(ln_fold_pack_run(P[i], P[i + 1], ln1w, ln1b, HID, hi, lo, l.s_qkv + q * HID, l.c_qkv + q * HID, st));
+      else RC(split2d_run(P[i], HID, HID, HID, hi, lo, HID, st));
+      COPYF(l.b_qkv + q * HID, P[i + 1], HID);
+      i += 2;
     }
     RC(split2d_run(P[i++], HID, HID, HID, l.o.hi, l.o.lo, HID, st));
     COPYF(l.b_o, P[i++], HID);
-    RC(split2d_run(P[i++], MLP, HID, HID, l.up.hi, l.up.lo, HID, st));
+    if (pl.ln_fold) RC(ln_fold_pack_run(P[i], P[i + 1], ln2w, ln2b, MLP, l.up.hi, l.up.lo, l.s_up, l.c_up, st));
+    else RC(split2d_run(P[i], MLP, HID, HID, l.up.hi, l.up.lo, HID, st));
+    ++i;
     COPYF(l.b_up, P[i++], MLP);
     RC(split2d_run(P[i++], HID, MLP, MLP, l.down.hi, l.down.lo, MLP, st));
     COPYF(l.b_down, P[i++], HID);
@@ -392,17 +439,20 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
     e.resid = pl.pos_perm; e.resid_ld = HID; e.resid_mod = live;
     e.rows_in = live; e.rows_out = TOK;
     e.out_f32 = pl.hidden; e.ldo = HID;
+    if (pl.ln_fold) produce_ln_operand(pl, e);
     RC(linear(pl, pl.a_patch, 256, B * live, 256, pl.w_patch, HID, e, st));
-    RC(fill_dummy_run(pl.hidden, pl.dummy, B, TOK, live, st));
+    if (pl.ln_fold) RC(fill_dummy_run(pl.hidden, pl.dummy, B, TOK, live, st, pl.ln.hi, pl.ln.lo, pl.stats));
+    else RC(fill_dummy_run(pl.hidden, pl.dummy, B, TOK, live, st));
   }
   if (last_stage == ST_EMBED) return 0;
   const int M = B * TOK;
   for (int l = 0; l < NLAYERS; ++l) {
     Plan::Layer& L = pl.L[l];
-    RC(layernorm_run(pl.hidden, L.ln1w, L.ln1b, B, TOK, TOK, 1e-12f, pl.ln.hi, pl.ln.lo, nullptr, st));
+    if (!pl.ln_fold) RC(layernorm_run(pl.hidden, L.ln1w, L.ln1b, B, TOK, TOK, 1e-12f, pl.ln.hi, pl.ln.lo, nullptr, st));
     {  // K5: fused QKV projection; Q|K row-major, V transposed per (frame, head)
       EpiParams e = epi0();
       e.bias = L.b_qkv;
+      if (pl.ln_fold) consume_ln_operand(pl, e, L.s_qkv, L.c_qkv);
       e.store = STORE_QKV; e.qk_cols = 2 * HID; e.tokens = TOK;
       e.out_hi = pl.qk.hi; e.out_lo = pl.qk.lo; e.ldo = 2 * HID;
       e.vt_hi = pl.vt.hi; e.vt_lo = pl.vt.lo;
@@ -440,19 +490,22 @@ static int forward(Plan& pl, const float* x, int B, float* pose, int last_stage,
     {  // K7: output projection + residual (in place on the fp32 residual stream)
       EpiParams e = epi0();
       e.bias = L.b_o; e.resid = pl.hidden; e.resid_ld = HID; e.out_f32 = pl.hidden; e.ldo = HID;
+      if (pl.ln_fold) produce_ln_operand(pl, e);
       if (last) RC(linear_live(pl, pl.ctx, HID, B, live, HID, L.o, HID, e, st));
       else RC(linear(pl, pl.ctx, HID, M, HID, L.o, HID, e, st));
     }
-    RC(layernorm_run(pl.hidden, L.ln2w, L.ln2b, B, TOK, TOK, 1e-12f, pl.ln.hi, pl.ln.lo, nullptr, st));
+    if (!pl.ln_fold) RC(layernorm_run(pl.hidden, L.ln2w, L.ln2b, B, TOK, TOK, 1e-12f, pl.ln.hi, pl.ln.lo, nullptr, st));
     {  // K8: MLP up + exact GELU
       EpiParams e = epi0();
-      e.bias = L.b_up; e.act = ACT_GELU; e.out_hi = pl.mlp.hi; e.out_lo = pl.mlp.lo; e.ldo = MLP;
+      e.bias = L.b_up; e.act = ACT_GELU;
+      if (pl.ln_fold) consume_ln_operand(pl, e, L.s_up, L.c_up); e.out_hi = pl.mlp.hi; e.out_lo = pl.mlp.lo; e.ldo = MLP;
       if (last) RC(linear_live(pl, pl.ln, HID, B, live, HID, L.up, MLP, e, st));
       else RC(linear(pl, pl.ln, HID, M, HID, L.up, MLP, e, st));
     }
     {  // K9: MLP down + residual
       EpiParams e = epi0();
       e.bias = L.b_down; e.resid = pl.hidden; e.resid_ld = HID; e.out_f32 = pl.hidden; e.ldo = HID;
+      if (pl.ln_fold && l + 1 < NLAYERS) produce_ln_operand(pl, e);     // the last layer feeds the final LayerNorm kernel
       if (last) RC(linear_live(pl, pl.mlp, MLP, B, live, MLP, L.down, HID, e, st));
       else RC(linear(pl, pl.mlp, MLP, M, MLP, L.down, HID, e, st));
     }

@@ -8,7 +8,7 @@ namespace eb {
 
 // kernels.cu / train_ops.cu
 int split2d_run(const float*, long long, long long, long long, __nv_bfloat16*, __nv_bfloat16*, long long, cudaStream_t);
-int fill_dummy_run(float*, const float*, int, int, int, cudaStream_t);
+int fill_dummy_run(float*, const float*, int, int, int, cudaStream_t, __nv_bfloat16* = nullptr, __nv_bfloat16* = nullptr, float2* = nullptr);
 int pos_permute_run(const float*, const float*, int, int, float*, float*, cudaStream_t);
 int pu_bridge_gate_run(const float*, int, int, const float*, int, int, long long, __nv_bfloat16*, __nv_bfloat16*,
                        cudaStream_t);

@@ -171,12 +171,14 @@ def test_per_joint_launch_path_agrees_with_persistent_chain(state_dicts):
             "print(net.predict_pose(x).flatten().tolist())")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for env in ({}, {"EGOTAP_PU": "steps", "EGOTAP_ATTN": "unfused", "EGOTAP_SKIP_DUMMY": "0"}):
+    # (the third run folds the six in-layer LayerNorm kernels into the GEMMs around them: opt-in EGOTAP_LN=fold)
+    for env in ({}, {"EGOTAP_PU": "steps", "EGOTAP_ATTN": "unfused", "EGOTAP_SKIP_DUMMY": "0"}, {"EGOTAP_LN": "fold"}):
         r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "oracle"))], capture_output=True,
                            text=True, env=dict(os.environ, **env), timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(torch.tensor(json.loads(r.stdout.strip().splitlines()[-1])))
     assert ((outs[0] - outs[1]).abs().max() / outs[1].abs().max()).item() < 2e-4
+    assert ((outs[0] - outs[2]).abs().max() / outs[2].abs().max()).item() < 2e-4
 
 
 def test_empty_ragged_and_odd_inputs(state_dicts):

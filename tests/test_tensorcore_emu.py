@@ -492,7 +492,11 @@ _INFER_CASES = [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
                 ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
                 ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"}),
                 # both opt-in kernels in the one-MMA bf16 mode (EMU_PREC is read by the child below, not by the library)
-                ("EgoCap", {"EGOTAP_ATTN": "wide", "EGOTAP_EPI": "coalesced", "EMU_PREC": "1"})]
+                ("EgoCap", {"EGOTAP_ATTN": "wide", "EGOTAP_EPI": "coalesced", "EMU_PREC": "1"}),
+                # two frames: the paired-SM GEMMs with the TMA epilogue (one frame runs on the single-SM tile configurations);
+                # the opt-in LayerNorm fold (EGOTAP_LN=fold: in-layer LayerNorms folded into the GEMMs around them) on both
+                ("UnrealEgo", {"EMU_BATCH": "2"}), ("UnrealEgo", {"EMU_BATCH": "2", "EGOTAP_LN": "fold"}),
+                ("EgoCap", {"EMU_BATCH": "2", "EMU_PREC": "1", "EGOTAP_LN": "fold"}), ("UnrealEgo", {"EGOTAP_LN": "fold"})]
 _INFER_CODE = r'''
 import ctypes as C, json, os, sys
 sys.path[:0] = %r
@@ -503,25 +507,26 @@ lib = C.CDLL(build_emu.build()); lib.egotap_b200_last_error.restype = C.c_char_p
 lib.emu_set_num_sms(32)
 pid = 0 if preset == "UnrealEgo" else 1
 prec = int(os.environ.get("EMU_PREC", "0"))
+nb = int(os.environ.get("EMU_BATCH", "1"))
 pb, wb = C.c_size_t(), C.c_size_t()
 lib.egotap_b200_plan_sizes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-assert lib.egotap_b200_plan_sizes(pid, prec, 1, C.byref(pb), C.byref(wb)) == 0
+assert lib.egotap_b200_plan_sizes(pid, prec, nb, C.byref(pb), C.byref(wb)) == 0
 packed = torch.zeros(pb.value + 1024, dtype=torch.uint8); work = torch.full((wb.value // 4 + 256,), float("nan"))
 al = lambda t: (t.data_ptr() + 1023) // 1024 * 1024
 plan = C.c_void_p()
 lib.egotap_b200_plan_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-assert lib.egotap_b200_plan_create(pid, prec, 1, al(packed), al(work), C.byref(plan)) == 0
+assert lib.egotap_b200_plan_create(pid, prec, nb, al(packed), al(work), C.byref(plan)) == 0
 sd = weights.make_state_dict(preset, seed=5)
 names = [lib.egotap_b200_param_name(pid, i).decode() for i in range(lib.egotap_b200_num_params(pid))]
 tens = [sd[n].float().contiguous() for n in names]
 arr = (C.c_void_p * len(tens))(*[t.data_ptr() for t in tens])
 lib.egotap_b200_pack_weights.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
 assert lib.egotap_b200_pack_weights(plan, arr, len(tens), None) == 0, lib.egotap_b200_last_error()
-x = synthetic_heatmaps(preset, 1, seed=1234, kind="gauss").contiguous()
+x = synthetic_heatmaps(preset, nb, seed=1234, kind="gauss").contiguous()
 nj = 16 if preset == "UnrealEgo" else 17
-pose = torch.full((1, nj, 3), float("nan"))
+pose = torch.full((nb, nj, 3), float("nan"))
 lib.egotap_b200_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-assert lib.egotap_b200_forward(plan, x.data_ptr(), 1, pose.data_ptr(), -1, None) == 0, lib.egotap_b200_last_error()
+assert lib.egotap_b200_forward(plan, x.data_ptr(), nb, pose.data_ptr(), -1, None) == 0, lib.egotap_b200_last_error()
 with torch.no_grad():
     ref = orc.forward(sd, x, preset)
 print("RESULT " + json.dumps(orc.parity_report(pose, ref)))
