@@ -42,7 +42,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit"
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -75,7 +75,20 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+        out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+        def num(r, i):
+            try:
+                return float(r[i])
+            except (IndexError, ValueError):
+                return None
+        # board power as nvidia-smi reports it (an average over about the last second, i.e. longer than a short timed region:
+        # a lower bound of the power inside it; tools/power_probe.py measures sustained loops -- DESIGN section 9.2)
+        pw = sorted(v for v in (num(r, 6) for r in self.rows) if v is not None)
+        lim = [v for v in (num(r, 7) for r in self.rows) if v is not None]
+        if pw:
+            out.update(power_w_smi_avg=round(pw[len(pw) // 2], 1), power_limit_w=round(max(lim), 1) if lim else None)
+        return out
 
 
 def time_oracle_cpu(preset, sd, steps, warmup, batch=CPU_SAMPLE_BATCH):
