@@ -29,14 +29,15 @@
 //   warp 0   TMA producer      warps 1, 2   MMA issuers (even / odd key tiles)      warp 3   tensor-memory allocation
 //   warps 4-11  softmax (pairs split the keys of a tile)
 //   warps 12-15  epilogue: O (double-buffered across items) / l -> bf16 hi/lo context rows
-// Two issuing warps (round 2, ncu source page of the single-issuer kernel): every tcgen05.mma costs its issuing warp ~40 cycles
-// of election / descriptor / R2UR instructions against 64 cycles of tensor-pipe work per 128 x 128 x 16 MMA; with the 96 MMAs of
-// a parity-mode tile on ONE warp that warp was busy ~3,900 of the ~4,300 cycles of a tile period and stalled on the MMA queue
-// only 12 % of its time -- instruction issue, not the tensor pipe or the softmax, set the period.  Warp 1 now issues S_g and
-// P V_g of the even tiles, warp 2 of the odd tiles.  Each S/P buffer is touched by one thread's MMAs only, so S_{g+2} still
-// follows P V_g in that thread's program order (no buffer-free barrier); the accumulation order of O across the two threads
-// is enforced with the existing pv_done barriers (P V_{g+1} is issued after P V_g has completed, which it has long before
-// P_{g+1} arrives).
+// Two issuing warps (round 2; ncu source page and cycle counters of the single-issuer kernel, profiles/r02g_attention_two_issuers.md):
+// every tcgen05.mma costs its issuing warp ~80 cycles of election / descriptor / R2UR instructions against 64 cycles of tensor-pipe
+// work per 128 x 128 x 16 MMA; with the 48 MMAs of a parity-mode tile on ONE warp that warp was busy ~3,800 of the ~4,300 cycles of
+// a tile period and stalled on the MMA queue only 12 % of its time -- instruction issue, not the tensor pipe or the softmax, set
+// the period.  Warp 1 now issues S_g and P V_g of the even tiles, warp 2 of the odd tiles.  Each S/P buffer is touched by one
+// thread's MMAs only, so S_{g+2} still follows P V_g in that thread's program order (no buffer-free barrier); the accumulation
+// order of O across the two threads is enforced with the existing pv_done barriers (P V_{g+1} is issued after P V_g has completed,
+// which it has long before P_{g+1} arrives).  Measured: bf16 mode 0.460 -> 0.424 ms per layer; the parity mode stays at 0.944 ms,
+// now bound by the L2 -> shared-memory stream of K / V (6.4 TB/s).
 #include "gemm.cuh"
 #include "host_util.cuh"
 #include "internal.h"
