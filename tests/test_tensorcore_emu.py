@@ -794,7 +794,10 @@ def test_tensor_core_kernels_with_late_tma_loads(be, latency):
         lib.emu_set_tma_latency(latency, 99)
         test_gemm_tile_configurations(be, 0, 1)
         test_gemm_tile_configurations(be, 3, 0)
+        test_gemm_transposed_operands(be, 4, 1)
         test_persistent_chain_kernel(5, 15, True)
+        test_fused_attention_backward_kernels(be)
+        test_persistent_bptt_kernel(be, 5, 15, True)
     finally:
         lib.emu_set_tma_latency(0, 0)
 
