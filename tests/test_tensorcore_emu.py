@@ -321,10 +321,11 @@ def test_gemm_transposed_operands(be, variant, prec):
 @pytest.mark.parametrize("prec", [1, 0])
 @pytest.mark.parametrize("variant", [""])
 def test_fused_attention_kernel(be, prec, variant):
-    """14 warps, ten mbarrier families, S and O double-buffered in tensor memory, P as the TS-form A operand, lazy rescale;
-    2 frames = 80 work items on the emulated 6-SM device, i.e. ~13 items per persistent CTA (phase parities wrap).
-    variant 'wide' (EGOTAP_ATTN=wide, csrc/attention_wide.cu): 128-key score tiles with a 64-key tail, P written over S,
-    one software pipeline across the work items of a CTA (odd tile count per item: buffers alternate between items)"""
+    """csrc/attention.cu: 16 warps (TMA producer, two MMA-issuing warps with their own kv_full barrier sets, 8 softmax, 4 epilogue
+    warps), a dozen mbarrier families, 128-key score tiles with a 64-key tail, S / P and O double-buffered in tensor memory, P
+    written over S as the TS-form A operand and handed over in two steps, lazy rescale, one software pipeline across the work
+    items of a CTA (odd tile count per item: buffers alternate between items); 2 frames = 80 work items on the emulated 6-SM
+    device, i.e. ~13 items per persistent CTA (phase parities wrap)"""
     emu, orc = be
     with _env("EGOTAP_ATTN", variant):
         _fused_attention_case(emu, orc, prec)
@@ -431,7 +432,7 @@ def test_whole_training_step_on_product_kernel_source():
         a, b = grads[k].flatten().double(), g_ref.flatten().double()
         # direction bound 0.999: ONE LeakyReLU' factor that flips at z ~ 0 (a 1e-5 forward difference is enough, e.g. between the
         # two attention kernels, which are equally accurate against fp64) moves the small gradients upstream of it by a few per
-        # cent -- measured: layer-2 query.bias 0.99948 with EGOTAP_ATTN=wide, 1.00000 without; an indexing / layout error gives << 0.99
+        # cent -- measured: layer-2 query.bias 0.99948 at worst; an indexing / layout error gives << 0.99
         assert float((a @ b) / (a.norm() * b.norm())) > 0.999, k
         assert abs(float(a.norm() / b.norm()) - 1) < 2e-2, k
 
@@ -490,9 +491,10 @@ def test_persistent_chain_kernel(frames, J, x3):
 
 _INFER_CASES = [("UnrealEgo", {}), ("EgoCap", {"EGOTAP_SKIP_DUMMY": "0"}),
                 ("UnrealEgo", {"EGOTAP_ATTN": "unfused", "EGOTAP_PU": "steps"}),
-                ("EgoCap", {"EGOTAP_SPLITK": "1"}), ("UnrealEgo", {"EGOTAP_ATTN": "wide"}),
-                # both opt-in kernels in the one-MMA bf16 mode (EMU_PREC is read by the child below, not by the library)
-                ("EgoCap", {"EGOTAP_ATTN": "wide", "EGOTAP_EPI": "coalesced", "EMU_PREC": "1"}),
+                ("EgoCap", {"EGOTAP_SPLITK": "1"}),
+                # the coalesced epilogue forced for every GEMM, in the one-MMA bf16 mode (EMU_PREC is read by the child below, not
+                # by the library)
+                ("EgoCap", {"EGOTAP_EPI": "coalesced", "EMU_PREC": "1"}),
                 # two frames: the paired-SM GEMMs with the TMA epilogue (one frame runs on the single-SM tile configurations);
                 # the opt-in LayerNorm fold (EGOTAP_LN=fold: in-layer LayerNorms folded into the GEMMs around them) on both
                 ("UnrealEgo", {"EMU_BATCH": "2"}), ("UnrealEgo", {"EMU_BATCH": "2", "EGOTAP_LN": "fold"}),
@@ -597,7 +599,7 @@ def test_whole_inference_path_on_product_source(preset, env, state_dicts):
     """egotap_b200_plan_create / pack_weights / forward -- the product's main entry points -- with every kernel executed
     from source on the emulation, against the CPU oracle (itself pinned to the reference): the default path (fused
     attention, persistent chain, last-layer dummy-row skipping), the A/B switches, the opt-in small-batch split-K of
-    the first FC block and the opt-in wide attention kernel.  Runs in a subprocess because most
+    the first FC block, the forced coalesced epilogue and the opt-in LayerNorm fold.  Runs in a subprocess because most
     switches are read from the environment once per process."""
     import json
     key = ("infer", _INFER_CASES.index((preset, env)))
@@ -663,7 +665,7 @@ print("RESULT " + json.dumps(dict(launches=lib.emu_set_dry_run(0), workspace_gb=
     ("infer", "UnrealEgo", 256, "bf16x3", ""),                # BASELINE config 2 (the bench default)
     ("infer", "EgoCap", 1024, "bf16", ""),                    # config 3 on one GPU
     ("infer", "UnrealEgo", 32, "bf16x3", "EGOTAP_SPLITK=1"),
-    ("infer", "UnrealEgo", 1024, "bf16x3", "EGOTAP_ATTN=wide EGOTAP_EPI=coalesced"),   # both opt-in kernels at the largest size
+    ("infer", "UnrealEgo", 1024, "bf16x3", "EGOTAP_EPI=coalesced"),   # the coalesced epilogue everywhere at the largest size
 ])
 def test_full_size_steps_pass_the_host_checks_and_launch_limits(kind, preset, batch, prec, extra):
     """Dry run at BASELINE.json's real batch sizes: the whole training step / inference forward is driven through the library
@@ -767,8 +769,6 @@ def test_tensor_core_kernels_do_not_depend_on_the_thread_schedule(be, mode):
         test_gemm_epilogue_modes(be, 4, 1)
         test_fused_attention_kernel(be, 0, "")
         test_fused_attention_kernel(be, 1, "")
-        test_fused_attention_kernel(be, 0, "wide")
-        test_fused_attention_kernel(be, 1, "wide")
         test_persistent_chain_kernel(5, 15, True)
         test_persistent_bptt_kernel(be, 5, 15, True)
         test_persistent_bptt_kernel(be, 150, 17, False)
