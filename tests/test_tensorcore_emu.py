@@ -539,7 +539,10 @@ _CHILD_PATHS = [_ROOT, os.path.join(_ROOT, "oracle"), os.path.join(os.path.dirna
 # test of the module runs and are collected by the tests that own them, so they overlap with the in-process tests
 # (the suite is CPU-only and the emulation is single-threaded).  EGOTAP_EMU_CHILD marks a child pytest.
 _BG = {}
-_HEAVY = ["test_whole_training_step_on_product_kernel_source", "test_engine_with_persistent_bptt_matches_per_joint_path"]
+_HEAVY = ["test_whole_training_step_on_product_kernel_source", "test_engine_with_persistent_bptt_matches_per_joint_path",
+          "test_tensor_core_kernels_do_not_depend_on_the_thread_schedule[reversed]",
+          "test_tensor_core_kernels_do_not_depend_on_the_thread_schedule[shuffled]",
+          "test_tensor_core_kernels_with_late_tma_loads[late4]", "test_tensor_core_kernels_with_late_tma_loads[late11]"]
 
 
 def _in_child():
@@ -762,6 +765,8 @@ def test_tensor_core_kernels_do_not_depend_on_the_thread_schedule(be, mode):
     """the warp-specialised kernels (GEMM incl. a paired-SM configuration, fused attention, both persistent chain kernels)
     with their threads scheduled in descending / reshuffled order: every hand-off between the TMA, MMA, softmax and
     epilogue warps must be carried by an mbarrier / named barrier, never by the order the warps happen to run in"""
+    if _heavy_in_parent("test_tensor_core_kernels_do_not_depend_on_the_thread_schedule[%s]" % {1: "reversed", 2: "shuffled"}[mode]):
+        return
     try:
         _set_schedule(mode)
         test_gemm_tile_configurations(be, 0, 1)
@@ -784,6 +789,8 @@ def test_tensor_core_kernels_with_late_tma_loads(be, latency):
     first two-issuer attention kernel failed on the B200 in the parity mode only (one set of kv_full barriers shared by two
     consuming warps, each seeing every other phase) while passing every prompt-load emulation run."""
     import ctypes as C
+    if _heavy_in_parent("test_tensor_core_kernels_with_late_tma_loads[late%d]" % latency):
+        return
     lib = _emu_lib()
     lib.emu_set_tma_latency.argtypes = [C.c_int, C.c_ulonglong]
     try:
