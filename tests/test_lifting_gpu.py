@@ -134,8 +134,8 @@ def test_batch_sizes_and_ragged_batches(state_dicts):
     # not bit-identical: at <= 32 frames the first FC block is split along its reduction dimension into a batch-dependent number
     # of chunks (fp32 summation order), which shows at the 1e-5 level of the fp32-parity mode (vs the oracle: ~1e-4)
     scale = full.abs().max().item()
-    assert (full[3:4] - one).abs().max().item() < 5e-5 * scale
-    assert (full[:5] - part).abs().max().item() < 5e-5 * scale
+    assert (full[3:4] - one).abs().max().item() < 1e-4 * scale       # measured 3e-5 (round 2, several boxes)
+    assert (full[:5] - part).abs().max().item() < 1e-4 * scale
     with torch.no_grad():
         ref = orc.forward(state_dicts(preset), x.cpu(), preset)
     assert orc.parity_report(full, ref)["rel"] <= 5e-4
